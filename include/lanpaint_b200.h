@@ -1,0 +1,189 @@
+/*
+ * lanpaint_b200 -- C ABI of the B200-native LanPaint Langevin hot path.
+ *
+ * The reference (scraed/LanPaint) is pure Python/PyTorch and has no FFI; this
+ * header is the boundary a maintainer would bind (ctypes stub in
+ * INTEGRATION.md).  Each entry point names the reference code it replaces,
+ * paths relative to the reference root.
+ *
+ * Conventions
+ *   - all tensors are fp32, contiguous, NC(T)HW; "per_sample" = C*spatial
+ *   - the mask is uint8, 1 = known / keep (the reference's latent_mask,
+ *     src/LanPaint/nodes.py:281-283), either full shape or [B,1,spatial]
+ *     broadcast over channels (mask_channel_stride = 0)
+ *   - per-sample scalars live in a device "coefficient table" of
+ *     LP_TABLE_STRIDE floats per row, built on the host by
+ *     lp_build_coef_table() -- this removes every exp/expm1/sqrt/where and
+ *     every host sync of src/LanPaint/lanpaint.py:205,232-254,295-328 from
+ *     the per-element path
+ *   - every device entry point is asynchronous on the caller's stream, does
+ *     not allocate, does not synchronise, is CUDA-graph capturable and
+ *     re-entrant; it returns an lp_status (never throws)
+ */
+#ifndef LANPAINT_B200_H_
+#define LANPAINT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LP_ABI_VERSION 1
+#define LP_TABLE_STRIDE 24 /* floats per table row, layout below */
+
+typedef void* lp_stream_t; /* a cudaStream_t / CUstream */
+
+typedef enum lp_status {
+  LP_OK = 0,
+  LP_ERR_INVALID = 1,   /* null pointer / negative size / bad flag combination */
+  LP_ERR_ALIGNMENT = 2, /* reserved: all paths fall back to scalar access instead */
+  LP_ERR_CUDA = 3,      /* launch failed; see lp_last_cuda_error() */
+  LP_ERR_UNSUPPORTED = 4
+} lp_status;
+
+/* Table row layout (floats).  Class 0 = free / regenerate region ("x branch",
+ * mask 0), class 1 = known region ("y branch", mask 1).
+ *   0 c_tgt      sqrt(abt)/(1-abt)          coefficient of the score target in C
+ *   1 S          model-space x = x_t * S    (VE: sqrt(1+sigma^2); flow: 1/(sqrt(abt)+sqrt(1-abt)))
+ *   2 inv_S
+ *   3 lam        Lambda
+ *   4 one_plus_lam
+ *   5 rep_noise  replace step: known = rep_noise*noise + rep_y*y
+ *   6 rep_y
+ *   7 corr       audio target correction c (1 = none)         [lanpaint.py:173-180]
+ *   8+8k .. 15+8k  class k: g (= A - 1/(1-abt)), dt, e_full, k_full, sd_full, e_half, k_half, sd_half
+ * where for an advance over h:  e = exp(-A h), k = (1-e)/A, sd = sqrt(D^2 (1-exp(-2 A h))/(2A)), D = sqrt(2)
+ * (src/LanPaint/lanpaint.py:232-254), full = dt, half = dt/2.
+ */
+enum {
+  LP_T_CTGT = 0, LP_T_S = 1, LP_T_INVS = 2, LP_T_LAM = 3, LP_T_ONEPLAM = 4,
+  LP_T_REPN = 5, LP_T_REPY = 6, LP_T_CORR = 7, LP_T_CLS0 = 8, LP_T_CLS1 = 16,
+  LP_C_G = 0, LP_C_DT = 1, LP_C_EF = 2, LP_C_KF = 3, LP_C_SF = 4, LP_C_EH = 5, LP_C_KH = 6, LP_C_SH = 7
+};
+
+/* Engine hyper-parameters: constructor of the reference engine,
+ * src/LanPaint/lanpaint.py:8-21. */
+typedef struct lp_hyper {
+  double step_size;     /* StepSize */
+  double lam;           /* Lambda */
+  double beta;          /* Beta */
+  double min_step_frac; /* MinStepFrac */
+  int32_t flow;         /* IS_FLUX or IS_FLOW */
+  int32_t reserved;
+} lp_hyper;
+
+typedef struct lp_dims {
+  int64_t n_rows;              /* table rows == samples B (or B*2 with the audio class split) */
+  int64_t per_row;             /* elements per table row (C*spatial for one sample) */
+  int64_t spatial;             /* elements per channel */
+  int64_t mask_row_stride;     /* mask elements between consecutive rows */
+  int64_t mask_channel_stride; /* 0 = mask broadcast over channels, spatial = full-shape mask */
+} lp_dims;
+
+/* How the Gaussian draws of src/LanPaint/lanpaint.py:252 (torch.randn_like on
+ * the global generator) are supplied. */
+typedef enum lp_rng_mode {
+  LP_RNG_TAPE = 0,   /* caller passes the draws as tensors (exact CPU-oracle parity) */
+  LP_RNG_PHILOX = 1, /* in-kernel Philox4x32-10, element i <- component i&3 of counter (i>>2, draw) */
+  LP_RNG_TORCH = 2   /* in-kernel Philox reproducing torch.randn_like's CUDA stream bit for bit */
+} lp_rng_mode;
+
+typedef struct lp_rng {
+  int32_t mode;          /* lp_rng_mode */
+  int32_t reserved;
+  const float* tape0;    /* TAPE: draw consumed first by the launch */
+  const float* tape1;    /* TAPE: draw consumed second (may be NULL if unused) */
+  uint64_t seed;         /* PHILOX/TORCH */
+  uint64_t draw0;        /* PHILOX: draw index; TORCH: philox offset of the first draw */
+  uint64_t draw1;        /* second draw index / offset */
+  const uint64_t* state; /* optional device pointer {seed, base}: if non-NULL, seed is read from
+                            it and base is added to draw0/draw1 (lets a captured CUDA graph be
+                            replayed with a fresh stream position) */
+} lp_rng;
+
+/* ---- library ---------------------------------------------------------- */
+int lp_abi_version(void);
+const char* lp_status_string(int status);
+int lp_last_cuda_error(void); /* cudaError_t of the last failed launch on this thread */
+
+/* ---- host: coefficient table ------------------------------------------- */
+/* Replaces LanPaint.prepare_step_size + the mask blend of A/D/dt + the
+ * exp/expm1/where/sqrt of advance_time_overdamped (lanpaint.py:81,205-214,
+ * 232-254,295-328).  Inputs are the reference's own per-sample fp32 values
+ * (abt, VE sigma: nodes.py:242-252) widened to double; arithmetic is fp64,
+ * results rounded once to fp32.  rep_noise/rep_y may be NULL (-> 0, 1);
+ * corr may be NULL (-> 1).  table_out: n_rows*LP_TABLE_STRIDE floats (host). */
+int lp_build_coef_table(const double* abt, const double* ve_sigma, const double* rep_noise,
+                        const double* rep_y, const double* corr, int64_t n_rows,
+                        const lp_hyper* hyper, float* table_out);
+
+/* Geometry of torch's CUDA randn kernel (ATen/native/cuda/DistributionTemplates.h:
+ * calc_execution_policy) for `numel` elements on `device`: grid blocks of 256
+ * threads and the philox offset increment one draw consumes. */
+int lp_torch_randn_geometry(int64_t numel, int device, int64_t* grid_out, uint64_t* increment_out);
+
+/* ---- device: hot path --------------------------------------------------- */
+/* mask_f32 > 0.5 -> uint8 (the binarise of nodes.py:281-283, done once). */
+int lp_pack_mask_f32(const float* mask_f32, uint8_t* mask_u8, int64_t n, int invert, lp_stream_t stream);
+
+/* Replace step + change of variables, lanpaint.py:85-99:
+ *   x_model = mask ? rep_noise*noise + rep_y*y : x
+ * written to x_model (may alias x) and, if non-NULL, x_copy. */
+int lp_prologue_f32(const float* x, const float* y, const float* noise, const uint8_t* mask,
+                    float* x_model, float* x_copy, const float* table, const lp_dims* dims,
+                    lp_stream_t stream);
+
+/* Flags of lp_substep_f32. */
+enum {
+  LP_SUBSTEP_FIRST = 1,     /* sub-step 0: no previous C, one full-dt advance (run_overdamped, args is None) */
+  LP_SUBSTEP_FUSE_NEXT = 2, /* also apply the first half-advance of the NEXT sub-step (uses the new C) */
+  LP_SUBSTEP_STORE_C = 4    /* write the new C even without FUSE_NEXT (un-fused / early-stop loops) */
+};
+
+/* One fused Langevin launch = everything between two model calls
+ * (lanpaint.py:113-142 -> langevin_dynamics :192-293 -> score_model :159-184,
+ * Coef_C :217-220, advance_time_overdamped :232-254, run_overdamped :274-286):
+ *   post-model half of sub-step i  [FIRST: C=Coef_C(x); x=adv(x,dt,C)
+ *                                   else : Cn=Coef_C(x); x+=(Cn-C)dt; x=adv(x,dt/2,C_old)]
+ *   + pre-model half of sub-step i+1 [x=adv(x,dt/2,Cn)] when FUSE_NEXT.
+ * x_model is read (the model's input) and overwritten with the next model
+ * input; c_state is read (unless FIRST) and written (FUSE_NEXT or STORE_C);
+ * x0/x0_big are the model's two heads (x0_big NULL or == x0: aliased);
+ * x_copy (optional) also receives the new x (the reference's
+ * input_x.copy_(x), lanpaint.py:156); x0e_out (optional) receives
+ * x_t + score, the LangevinState.x0 the early stopper watches.
+ * Consumes 2 draws with FUSE_NEXT, else 1. */
+int lp_substep_f32(float* x_model, const float* x0, const float* x0_big, const float* y,
+                   const uint8_t* mask, float* c_state, float* x_copy, float* x0e_out,
+                   const float* table, const lp_dims* dims, const lp_rng* rng, int flags,
+                   lp_stream_t stream);
+
+/* The un-fused building block: one exact OU advance of the model-space state,
+ *   x_t = x/S;  x_t = e x_t + k C + sd xi;  x = x_t S
+ * over dt (half = 0) or dt/2 (half = 1) -- advance_time_overdamped,
+ * lanpaint.py:232-254.  Consumes 1 draw (rng->draw0 / tape0). */
+int lp_advance_f32(float* x_model, const float* c_state, const uint8_t* mask, const float* table,
+                   const lp_dims* dims, const lp_rng* rng, int half, lp_stream_t stream);
+
+/* out = mask ? y : model_out   (lanpaint.py:151-154). */
+int lp_epilogue_f32(const float* model_out, const float* y, const uint8_t* mask, float* out,
+                    const lp_dims* dims, lp_stream_t stream);
+
+/* ---- device: utilities (tests, bench) ---------------------------------- */
+/* out[i] ~ N(0,1) with the given rng (PHILOX or TORCH; draw0 only). */
+int lp_fill_normal_f32(float* out, int64_t n, const lp_rng* rng, lp_stream_t stream);
+
+/* Synthetic pointwise two-head denoiser used by bench.py:
+ *   h0 = a0*x + b0*tanh(x) + c0 ;  h1 = a1*x + c1     coef = {a0,b0,c0,a1,c1} */
+int lp_synth_denoiser_f32(const float* x, float* h0, float* h1, int64_t n, const float* coef5_host,
+                          lp_stream_t stream);
+
+/* Writes `bytes` of scratch (> L2) to evict the working set between launches. */
+int lp_l2_flush(void* scratch, size_t bytes, lp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LANPAINT_B200_H_ */

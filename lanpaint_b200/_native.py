@@ -1,0 +1,102 @@
+"""ctypes binding of include/lanpaint_b200.h.
+
+There is deliberately no fallback: if the library is missing or a call fails
+the caller gets an exception.  (The product never routes through `oracle/`.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "liblanpaint_b200.so")
+
+ABI_VERSION = 1
+TABLE_STRIDE = 24
+
+RNG_TAPE, RNG_PHILOX, RNG_TORCH = 0, 1, 2
+SUBSTEP_FIRST, SUBSTEP_FUSE_NEXT, SUBSTEP_STORE_C = 1, 2, 4
+
+# every symbol include/lanpaint_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = (
+    "lp_abi_version", "lp_status_string", "lp_last_cuda_error", "lp_build_coef_table",
+    "lp_torch_randn_geometry", "lp_pack_mask_f32", "lp_prologue_f32", "lp_substep_f32", "lp_advance_f32",
+    "lp_epilogue_f32", "lp_fill_normal_f32", "lp_synth_denoiser_f32", "lp_l2_flush",
+)
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class Hyper(C.Structure):
+    _fields_ = [("step_size", C.c_double), ("lam", C.c_double), ("beta", C.c_double),
+                ("min_step_frac", C.c_double), ("flow", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Dims(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("per_row", C.c_int64), ("spatial", C.c_int64),
+                ("mask_row_stride", C.c_int64), ("mask_channel_stride", C.c_int64)]
+
+
+class Rng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("reserved", C.c_int32), ("tape0", C.c_void_p), ("tape1", C.c_void_p),
+                ("seed", C.c_uint64), ("draw0", C.c_uint64), ("draw1", C.c_uint64), ("state", C.c_void_p)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (once) and type the library.  Raises NativeError when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise NativeError(
+            f"{_LIB_PATH} is missing: build it with `python -m lanpaint_b200.build` "
+            "(nvcc, sm_100a).  lanpaint_b200 has no CPU or eager-PyTorch fallback.")
+    lib = C.CDLL(_LIB_PATH)
+    p, i64, u64, i32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int
+    lib.lp_abi_version.restype = i32
+    lib.lp_abi_version.argtypes = []
+    lib.lp_status_string.restype = C.c_char_p
+    lib.lp_status_string.argtypes = [i32]
+    lib.lp_last_cuda_error.restype = i32
+    lib.lp_last_cuda_error.argtypes = []
+    lib.lp_build_coef_table.restype = i32
+    lib.lp_build_coef_table.argtypes = [p, p, p, p, p, i64, C.POINTER(Hyper), p]
+    lib.lp_torch_randn_geometry.restype = i32
+    lib.lp_torch_randn_geometry.argtypes = [i64, i32, C.POINTER(i64), C.POINTER(u64)]
+    lib.lp_pack_mask_f32.restype = i32
+    lib.lp_pack_mask_f32.argtypes = [p, p, i64, i32, p]
+    lib.lp_prologue_f32.restype = i32
+    lib.lp_prologue_f32.argtypes = [p, p, p, p, p, p, p, C.POINTER(Dims), p]
+    lib.lp_substep_f32.restype = i32
+    lib.lp_substep_f32.argtypes = [p, p, p, p, p, p, p, p, p, C.POINTER(Dims), C.POINTER(Rng), i32, p]
+    lib.lp_advance_f32.restype = i32
+    lib.lp_advance_f32.argtypes = [p, p, p, p, C.POINTER(Dims), C.POINTER(Rng), i32, p]
+    lib.lp_epilogue_f32.restype = i32
+    lib.lp_epilogue_f32.argtypes = [p, p, p, p, C.POINTER(Dims), p]
+    lib.lp_fill_normal_f32.restype = i32
+    lib.lp_fill_normal_f32.argtypes = [p, i64, C.POINTER(Rng), p]
+    lib.lp_synth_denoiser_f32.restype = i32
+    lib.lp_synth_denoiser_f32.argtypes = [p, p, p, i64, p, p]
+    lib.lp_l2_flush.restype = i32
+    lib.lp_l2_flush.argtypes = [p, C.c_size_t, p]
+    v = lib.lp_abi_version()
+    if v != ABI_VERSION:
+        raise NativeError(f"ABI mismatch: library {v}, binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        lib = load()
+        msg = lib.lp_status_string(rc).decode()
+        raise NativeError(f"{what}: {msg} (status {rc}, cudaError {lib.lp_last_cuda_error()})")

@@ -1,0 +1,779 @@
+// lanpaint_b200: sm_100a kernels for LanPaint's inner Langevin loop + their C ABI.
+//
+// One fused launch per Langevin sub-step replaces the ~89 element-wise ATen
+// kernels the reference issues between two model calls
+// (src/LanPaint/lanpaint.py:113-142,159-184,192-293).  The work is a pure
+// HBM stream: 28+1/C bytes per latent element, a dozen FMAs, two Gaussian
+// draws.  So the design rules are the streaming ones: 128-bit coalesced
+// accesses, one table row of host-precomputed coefficients per sample instead
+// of per-element exp/expm1/sqrt, Philox + Box-Muller in registers, no shared
+// memory round trip, no host synchronisation, graph-capturable.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lanpaint_b200.h"
+
+namespace lp {
+
+thread_local int g_last_cuda_error = 0;
+
+constexpr int kBlock = 256;
+
+// ----------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011; same constants/round structure as cuRAND's
+// curand_philox4x32_x.h so LP_RNG_TORCH can reproduce torch.randn bit for bit)
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox_round(uint4 c, uint2 k) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c.x);
+  const uint32_t lo0 = 0xD2511F53u * c.x;
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z);
+  const uint32_t lo1 = 0xCD9E8D57u * c.z;
+  return make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    c = philox_round(c, k);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return philox_round(c, k);
+}
+
+// Box-Muller with exactly cuRAND's arithmetic (curand_normal.h:_curand_box_muller):
+// precise logf / sqrtf, fast __sincosf.  Used by LP_RNG_TORCH.
+__device__ __forceinline__ float2 box_muller_curand(uint32_t a, uint32_t b) {
+  const float u = a * 2.3283064e-10f + (2.3283064e-10f / 2);
+  const float v = b * (2.3283064e-10f * 6.2831855f) + ((2.3283064e-10f * 6.2831855f) / 2);
+  const float s = sqrtf(-2.0f * logf(u));
+  float2 r;
+  __sincosf(v, &r.x, &r.y);
+  r.x *= s;
+  r.y *= s;
+  return r;
+}
+
+// Cheaper variant for LP_RNG_PHILOX: MUFU lg2 / sqrt / sin / cos only.
+__device__ __forceinline__ float2 box_muller_fast(uint32_t a, uint32_t b) {
+  const float u = a * 2.3283064e-10f + (2.3283064e-10f / 2);  // (0, 1]
+  const float v = b * (2.3283064e-10f * 6.2831855f) + ((2.3283064e-10f * 6.2831855f) / 2);
+  float s;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(-2.0f * __logf(u)));
+  float2 r;
+  __sincosf(v, &r.x, &r.y);
+  r.x *= s;
+  r.y *= s;
+  return r;
+}
+
+template <bool kCurandExact>
+__device__ __forceinline__ float4 normal4(uint4 r) {
+  const float2 p = kCurandExact ? box_muller_curand(r.x, r.y) : box_muller_fast(r.x, r.y);
+  const float2 q = kCurandExact ? box_muller_curand(r.z, r.w) : box_muller_fast(r.z, r.w);
+  return make_float4(p.x, p.y, q.x, q.y);
+}
+
+// LP_RNG_PHILOX: element i <- component (i & 3) of Philox(counter = {i>>2, draw}, key = seed).
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t draw, uint32_t vec_index) {
+  const uint4 c = make_uint4(vec_index, 0u, (uint32_t)draw, (uint32_t)(draw >> 32));
+  const uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  return normal4<false>(philox4x32_10(c, k));
+}
+
+// LP_RNG_TORCH: what curand_init(seed, subsequence, offset) + the (call)-th curand_normal4 yields
+// when offset is a multiple of 4 (it always is for torch's generator).
+__device__ __forceinline__ float4 torch_normal4(uint64_t seed, uint64_t offset, uint32_t subsequence,
+                                                uint32_t call) {
+  const uint64_t ctr = (offset >> 2) + call;
+  const uint4 c = make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), subsequence, 0u);
+  const uint2 k = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  return normal4<true>(philox4x32_10(c, k));
+}
+
+__device__ __forceinline__ float pick(const float4& v, uint32_t j) {
+  return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
+}
+
+// ----------------------------------------------------------------------------
+// per-row coefficients (see LP_T_* in lanpaint_b200.h)
+// ----------------------------------------------------------------------------
+template <bool kFirst, bool kNext>
+struct RowCoef {
+  float c_tgt, S, inv_S, lam, one_plus_lam, corr;
+  float g[2], dt[2], e1[2], k1[2], s1[2];  // advance #1: full dt when kFirst, else half
+  float e2[2], k2[2], s2[2];               // advance #2 (only when kNext): always half
+
+  __device__ __forceinline__ void load(const float* __restrict__ t) {
+    c_tgt = __ldg(t + LP_T_CTGT);
+    S = __ldg(t + LP_T_S);
+    inv_S = __ldg(t + LP_T_INVS);
+    lam = __ldg(t + LP_T_LAM);
+    one_plus_lam = __ldg(t + LP_T_ONEPLAM);
+    corr = __ldg(t + LP_T_CORR);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float* c = t + LP_T_CLS0 + 8 * k;
+      g[k] = __ldg(c + LP_C_G);
+      dt[k] = __ldg(c + LP_C_DT);
+      e1[k] = __ldg(c + (kFirst ? LP_C_EF : LP_C_EH));
+      k1[k] = __ldg(c + (kFirst ? LP_C_KF : LP_C_KH));
+      s1[k] = __ldg(c + (kFirst ? LP_C_SF : LP_C_SH));
+      e2[k] = __ldg(c + LP_C_EH);
+      k2[k] = __ldg(c + LP_C_KH);
+      s2[k] = __ldg(c + LP_C_SH);
+    }
+  }
+};
+
+// The whole per-element update between two model calls.
+//   x      model-space state (in: what the model just saw; out: what it sees next)
+//   cprev  drift constant C of the previous sub-step (ignored when kFirst)
+//   returns the new C through cnew and x_t + score through x0e
+// Reference: score_model lanpaint.py:182-184, Coef_C :217-220,
+// advance_time_overdamped :232-254, run_overdamped :274-286.
+template <bool kFirst, bool kNext>
+__device__ __forceinline__ void substep_element(float& x, float x0, float x0b, float y, float cprev,
+                                                bool known, float xi1, float xi2,
+                                                const RowCoef<kFirst, kNext>& t, float& cnew,
+                                                float& x0e) {
+  // per-class coefficients by select (constant indices keep the row in registers)
+  const float g = known ? t.g[1] : t.g[0];
+  const float dt = known ? t.dt[1] : t.dt[0];
+  const float e1 = known ? t.e1[1] : t.e1[0];
+  const float k1 = known ? t.k1[1] : t.k1[0];
+  const float s1 = known ? t.s1[1] : t.s1[0];
+  const float e2 = known ? t.e2[1] : t.e2[0];
+  const float k2 = known ? t.k2[1] : t.k2[0];
+  const float s2 = known ? t.s2[1] : t.s2[0];
+  if (t.corr != 1.0f) {  // audio rows only (lanpaint.py:173-180); uniform per row
+    x0 = fmaf(t.corr, x0 - x, x);
+    x0b = fmaf(t.corr, x0b - x, x);
+  }
+  float xt = x * t.inv_S;
+  // x_t + score: free region -> x0 ; known region -> (1+lam) y - lam x0_BIG
+  const float tgt = known ? fmaf(-t.lam, x0b, t.one_plus_lam * y) : x0;
+  const float cn = fmaf(t.c_tgt, tgt, g * xt);
+  if (kFirst) {
+    xt = fmaf(e1, xt, fmaf(k1, cn, s1 * xi1));
+  } else {
+    xt = fmaf(cn - cprev, dt, xt);
+    xt = fmaf(e1, xt, fmaf(k1, cprev, s1 * xi1));  // old C on purpose (lanpaint.py:283-284)
+  }
+  if (kNext) xt = fmaf(e2, xt, fmaf(k2, cn, s2 * xi2));
+  x = xt * t.S;
+  cnew = cn;
+  x0e = tgt;
+}
+
+struct Geometry {
+  uint32_t total;     // B * per_row
+  uint32_t per_row;   // elements per table row
+  uint32_t spatial;   // elements per channel
+  uint32_t mask_row_stride;
+  uint32_t mask_channel_stride;
+};
+
+__device__ __forceinline__ void locate(const Geometry& g, uint32_t i, uint32_t& row, uint32_t& mask_index) {
+  row = i / g.per_row;
+  const uint32_t r = i - row * g.per_row;
+  const uint32_t ch = r / g.spatial;
+  const uint32_t s = r - ch * g.spatial;
+  mask_index = row * g.mask_row_stride + ch * g.mask_channel_stride + s;
+}
+
+struct SubstepArgs {
+  float* x;
+  const float* x0;
+  const float* x0b;
+  const float* y;
+  const uint8_t* mask;
+  float* c;
+  float* x_copy;
+  float* x0e;
+  const float* table;
+  const float* tape0;
+  const float* tape1;
+  const uint64_t* rng_state;
+  uint64_t seed, draw0, draw1;
+  Geometry g;
+  uint32_t torch_T;  // threads of torch's randn grid (LP_RNG_TORCH)
+  int store_c;       // write C even when the next half-advance is not fused
+};
+
+template <int N>
+struct Vec;
+template <>
+struct Vec<1> {
+  using F = float;
+  using M = uint8_t;
+};
+template <>
+struct Vec<4> {
+  using F = float4;
+  using M = uchar4;
+};
+
+template <int N>
+__device__ __forceinline__ void load_f(const float* p, uint32_t i, float (&v)[N]) {
+  if (N == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p + i);
+    v[0] = t.x; v[1 % N] = t.y; v[2 % N] = t.z; v[3 % N] = t.w;
+  } else {
+    v[0] = p[i];
+  }
+}
+template <int N>
+__device__ __forceinline__ void load_f_ro(const float* __restrict__ p, uint32_t i, float (&v)[N]) {
+  if (N == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
+    v[0] = t.x; v[1 % N] = t.y; v[2 % N] = t.z; v[3 % N] = t.w;
+  } else {
+    v[0] = __ldg(p + i);
+  }
+}
+template <int N>
+__device__ __forceinline__ void store_f(float* p, uint32_t i, const float (&v)[N]) {
+  if (N == 4) {
+    *reinterpret_cast<float4*>(p + i) = make_float4(v[0], v[1 % N], v[2 % N], v[3 % N]);
+  } else {
+    p[i] = v[0];
+  }
+}
+template <int N>
+__device__ __forceinline__ void load_m(const uint8_t* __restrict__ p, uint32_t i, bool (&v)[N]) {
+  if (N == 4) {
+    const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(p + i));
+    v[0] = t.x != 0; v[1 % N] = t.y != 0; v[2 % N] = t.z != 0; v[3 % N] = t.w != 0;
+  } else {
+    v[0] = __ldg(p + i) != 0;
+  }
+}
+
+// ---- TAPE / PHILOX: one N-wide vector per thread ---------------------------
+template <int N, int kRng, bool kFirst, bool kNext>
+__global__ void __launch_bounds__(kBlock) substep_kernel(const SubstepArgs a) {
+  const uint32_t v = blockIdx.x * kBlock + threadIdx.x;
+  const uint32_t i = v * N;
+  if (i >= a.g.total) return;
+  uint32_t row, mi;
+  locate(a.g, i, row, mi);
+
+  float x[N], x0[N], x0b[N], y[N], cp[N], cn[N], te[N], xi1[N], xi2[N];
+  bool known[N];
+  load_f<N>(a.x, i, x);
+  load_f_ro<N>(a.x0, i, x0);
+  if (a.x0b != a.x0) {
+    load_f_ro<N>(a.x0b, i, x0b);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) x0b[j] = x0[j];
+  }
+  load_f_ro<N>(a.y, i, y);
+  load_m<N>(a.mask, mi, known);
+  if (!kFirst) {
+    load_f<N>(a.c, i, cp);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) cp[j] = 0.f;
+  }
+
+  if (kRng == LP_RNG_TAPE) {
+    load_f_ro<N>(a.tape0, i, xi1);
+    if (kNext) {
+      load_f_ro<N>(a.tape1, i, xi2);
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) xi2[j] = 0.f;
+    }
+  } else {
+    uint64_t seed = a.seed, d0 = a.draw0, d1 = a.draw1;
+    if (a.rng_state) {
+      seed = a.rng_state[0];
+      d0 += a.rng_state[1];
+      d1 += a.rng_state[1];
+    }
+    const float4 n1 = philox_normal4(seed, d0, i >> 2);
+    float4 n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kNext) n2 = philox_normal4(seed, d1, i >> 2);
+    if (N == 4) {
+      xi1[0] = n1.x; xi1[1 % N] = n1.y; xi1[2 % N] = n1.z; xi1[3 % N] = n1.w;
+      xi2[0] = n2.x; xi2[1 % N] = n2.y; xi2[2 % N] = n2.z; xi2[3 % N] = n2.w;
+    } else {
+      xi1[0] = pick(n1, i & 3);
+      xi2[0] = pick(n2, i & 3);
+    }
+  }
+
+  RowCoef<kFirst, kNext> t;
+  t.load(a.table + (size_t)row * LP_TABLE_STRIDE);
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+    substep_element<kFirst, kNext>(x[j], x0[j], x0b[j], y[j], cp[j], known[j], xi1[j], xi2[j], t, cn[j], te[j]);
+
+  store_f<N>(a.x, i, x);
+  if (kNext || a.store_c) store_f<N>(a.c, i, cn);
+  if (a.x_copy) store_f<N>(a.x_copy, i, x);
+  if (a.x0e) store_f<N>(a.x0e, i, te);
+}
+
+// ---- TORCH: torch.randn_like's own thread<->element mapping -----------------
+// thread t of T handles elements t, t+T, t+2T, t+3T (one curand_normal4) per
+// 4T-stride iteration, exactly like distribution_elementwise_grid_stride_kernel
+// (ATen/native/cuda/DistributionTemplates.h), so one Philox call feeds 4
+// elements and the stream matches the eager reference on the same generator.
+template <bool kFirst, bool kNext>
+__global__ void __launch_bounds__(kBlock) substep_torch_kernel(const SubstepArgs a) {
+  const uint32_t T = a.torch_T;
+  const uint32_t tid = blockIdx.x * kBlock + threadIdx.x;
+  if (tid >= T) return;
+  uint64_t seed = a.seed, o0 = a.draw0, o1 = a.draw1;
+  if (a.rng_state) {
+    seed = a.rng_state[0];
+    o0 += a.rng_state[1];
+    o1 += a.rng_state[1];
+  }
+  uint32_t call = 0;
+  for (uint64_t base = tid; base < a.g.total; base += 4ull * T, ++call) {
+    const float4 n1 = torch_normal4(seed, o0, tid, call);
+    float4 n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kNext) n2 = torch_normal4(seed, o1, tid, call);
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const uint64_t li = base + (uint64_t)ii * T;
+      if (li >= a.g.total) break;
+      const uint32_t i = (uint32_t)li;
+      uint32_t row, mi;
+      locate(a.g, i, row, mi);
+      RowCoef<kFirst, kNext> t;
+      t.load(a.table + (size_t)row * LP_TABLE_STRIDE);
+      float x = a.x[i];
+      const float x0 = __ldg(a.x0 + i);
+      const float x0b = __ldg(a.x0b + i);
+      const float y = __ldg(a.y + i);
+      const bool known = __ldg(a.mask + mi) != 0;
+      const float cp = kFirst ? 0.f : a.c[i];
+      float cn, te;
+      substep_element<kFirst, kNext>(x, x0, x0b, y, cp, known, pick(n1, ii), pick(n2, ii), t, cn, te);
+      a.x[i] = x;
+      if (kNext || a.store_c) a.c[i] = cn;
+      if (a.x_copy) a.x_copy[i] = x;
+      if (a.x0e) a.x0e[i] = te;
+    }
+  }
+}
+
+// ---- un-fused OU advance (advance_time_overdamped, lanpaint.py:232-254) --------
+struct AdvanceArgs {
+  float* x;
+  const float* c;
+  const uint8_t* mask;
+  const float* table;
+  const float* tape0;
+  const uint64_t* rng_state;
+  uint64_t seed, draw0;
+  Geometry g;
+  uint32_t torch_T;
+  int half;
+};
+
+__device__ __forceinline__ float advance_element(float x, float c, bool known, float xi,
+                                                 const float* __restrict__ t, int half) {
+  const float* k = t + (known ? LP_T_CLS1 : LP_T_CLS0);
+  const float e = __ldg(k + (half ? LP_C_EH : LP_C_EF));
+  const float kk = __ldg(k + (half ? LP_C_KH : LP_C_KF));
+  const float sd = __ldg(k + (half ? LP_C_SH : LP_C_SF));
+  const float xt = x * __ldg(t + LP_T_INVS);
+  return fmaf(e, xt, fmaf(kk, c, sd * xi)) * __ldg(t + LP_T_S);
+}
+
+template <int kRng>
+__global__ void __launch_bounds__(kBlock) advance_kernel(const AdvanceArgs a) {
+  const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= a.g.total) return;
+  uint32_t row, mi;
+  locate(a.g, i, row, mi);
+  float xi;
+  if (kRng == LP_RNG_TAPE) {
+    xi = __ldg(a.tape0 + i);
+  } else {
+    uint64_t seed = a.seed, d0 = a.draw0;
+    if (a.rng_state) {
+      seed = a.rng_state[0];
+      d0 += a.rng_state[1];
+    }
+    xi = pick(philox_normal4(seed, d0, i >> 2), i & 3);
+  }
+  a.x[i] = advance_element(a.x[i], __ldg(a.c + i), __ldg(a.mask + mi) != 0, xi,
+                           a.table + (size_t)row * LP_TABLE_STRIDE, a.half);
+}
+
+__global__ void __launch_bounds__(kBlock) advance_torch_kernel(const AdvanceArgs a) {
+  const uint32_t T = a.torch_T;
+  const uint32_t tid = blockIdx.x * kBlock + threadIdx.x;
+  if (tid >= T) return;
+  uint64_t seed = a.seed, o0 = a.draw0;
+  if (a.rng_state) {
+    seed = a.rng_state[0];
+    o0 += a.rng_state[1];
+  }
+  uint32_t call = 0;
+  for (uint64_t base = tid; base < a.g.total; base += 4ull * T, ++call) {
+    const float4 n1 = torch_normal4(seed, o0, tid, call);
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const uint64_t li = base + (uint64_t)ii * T;
+      if (li >= a.g.total) break;
+      const uint32_t i = (uint32_t)li;
+      uint32_t row, mi;
+      locate(a.g, i, row, mi);
+      a.x[i] = advance_element(a.x[i], __ldg(a.c + i), __ldg(a.mask + mi) != 0, pick(n1, ii),
+                               a.table + (size_t)row * LP_TABLE_STRIDE, a.half);
+    }
+  }
+}
+
+// ---- prologue / epilogue / utilities ----------------------------------------
+template <int N>
+__global__ void __launch_bounds__(kBlock) prologue_kernel(const float* x, const float* __restrict__ y,
+                                                          const float* __restrict__ noise,
+                                                          const uint8_t* __restrict__ mask, float* x_model,
+                                                          float* x_copy, const float* __restrict__ table,
+                                                          Geometry g) {
+  const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
+  if (i >= g.total) return;
+  uint32_t row, mi;
+  locate(g, i, row, mi);
+  const float rn = __ldg(table + (size_t)row * LP_TABLE_STRIDE + LP_T_REPN);
+  const float ry = __ldg(table + (size_t)row * LP_TABLE_STRIDE + LP_T_REPY);
+  float xv[N], yv[N], nv[N];
+  bool known[N];
+  load_f<N>(x, i, xv);
+  load_f_ro<N>(y, i, yv);
+  load_f_ro<N>(noise, i, nv);
+  load_m<N>(mask, mi, known);
+#pragma unroll
+  for (int j = 0; j < N; ++j) xv[j] = known[j] ? fmaf(rn, nv[j], ry * yv[j]) : xv[j];
+  store_f<N>(x_model, i, xv);
+  if (x_copy) store_f<N>(x_copy, i, xv);
+}
+
+template <int N>
+__global__ void __launch_bounds__(kBlock) epilogue_kernel(const float* __restrict__ model_out,
+                                                          const float* __restrict__ y,
+                                                          const uint8_t* __restrict__ mask, float* out,
+                                                          Geometry g) {
+  const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
+  if (i >= g.total) return;
+  uint32_t row, mi;
+  locate(g, i, row, mi);
+  float ov[N], yv[N];
+  bool known[N];
+  load_f_ro<N>(model_out, i, ov);
+  load_f_ro<N>(y, i, yv);
+  load_m<N>(mask, mi, known);
+#pragma unroll
+  for (int j = 0; j < N; ++j) ov[j] = known[j] ? yv[j] : ov[j];
+  store_f<N>(out, i, ov);
+}
+
+__global__ void __launch_bounds__(kBlock) pack_mask_kernel(const float* __restrict__ m, uint8_t* out,
+                                                           uint32_t n, int invert) {
+  const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  const bool hi = __ldg(m + i) > 0.5f;
+  out[i] = (hi != (invert != 0)) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(kBlock) fill_normal_philox_kernel(float* out, uint32_t n, uint64_t seed,
+                                                                    uint64_t draw, const uint64_t* st) {
+  const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
+  if (i >= n) return;
+  if (st) {
+    seed = st[0];
+    draw += st[1];
+  }
+  out[i] = pick(philox_normal4(seed, draw, i >> 2), i & 3);
+}
+
+__global__ void __launch_bounds__(kBlock) fill_normal_torch_kernel(float* out, uint32_t n, uint64_t seed,
+                                                                   uint64_t offset, const uint64_t* st,
+                                                                   uint32_t T) {
+  const uint32_t tid = blockIdx.x * kBlock + threadIdx.x;
+  if (tid >= T) return;
+  if (st) {
+    seed = st[0];
+    offset += st[1];
+  }
+  uint32_t call = 0;
+  for (uint64_t base = tid; base < n; base += 4ull * T, ++call) {
+    const float4 r = torch_normal4(seed, offset, tid, call);
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const uint64_t li = base + (uint64_t)ii * T;
+      if (li < n) out[li] = pick(r, ii);
+    }
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(kBlock) synth_denoiser_kernel(const float* __restrict__ x, float* h0,
+                                                                float* h1, uint32_t n, float a0, float b0,
+                                                                float c0, float a1, float c1) {
+  const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
+  if (i >= n) return;
+  float xv[N], u[N], w[N];
+  load_f_ro<N>(x, i, xv);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    u[j] = fmaf(a0, xv[j], fmaf(b0, tanhf(xv[j]), c0));
+    w[j] = fmaf(a1, xv[j], c1);
+  }
+  store_f<N>(h0, i, u);
+  if (h1) store_f<N>(h1, i, w);
+}
+
+// ----------------------------------------------------------------------------
+// host helpers
+// ----------------------------------------------------------------------------
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+inline int check_launch() {
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_last_cuda_error = static_cast<int>(e);
+    return LP_ERR_CUDA;
+  }
+  return LP_OK;
+}
+
+inline int make_geometry(const lp_dims* d, Geometry& g) {
+  if (!d || d->n_rows < 0 || d->per_row <= 0 || d->spatial <= 0) return LP_ERR_INVALID;
+  if (d->per_row % d->spatial != 0) return LP_ERR_INVALID;
+  if (d->mask_row_stride < 0 || d->mask_channel_stride < 0) return LP_ERR_INVALID;
+  const int64_t total = d->n_rows * d->per_row;
+  const int64_t mask_extent = d->n_rows * d->mask_row_stride + d->per_row;  // loose upper bound
+  if (total >= (int64_t(1) << 31) || mask_extent >= (int64_t(1) << 31)) return LP_ERR_UNSUPPORTED;
+  g.total = static_cast<uint32_t>(total);
+  g.per_row = static_cast<uint32_t>(d->per_row);
+  g.spatial = static_cast<uint32_t>(d->spatial);
+  g.mask_row_stride = static_cast<uint32_t>(d->mask_row_stride);
+  g.mask_channel_stride = static_cast<uint32_t>(d->mask_channel_stride);
+  return LP_OK;
+}
+
+// 128-bit path needs every row / channel / mask offset to stay 4-aligned.
+inline bool geometry_vec4(const Geometry& g, const uint8_t* mask) {
+  return g.per_row % 4 == 0 && g.spatial % 4 == 0 && g.mask_row_stride % 4 == 0 &&
+         g.mask_channel_stride % 4 == 0 && aligned4(mask);
+}
+
+inline unsigned blocks_for(uint32_t n_threads) { return (n_threads + kBlock - 1) / kBlock; }
+
+int torch_grid(int64_t numel, int device, int64_t* grid, uint64_t* inc) {
+  if (numel <= 0) return LP_ERR_INVALID;
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) return LP_ERR_CUDA;
+  }
+  int sms = 0, tpsm = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&tpsm, cudaDevAttrMaxThreadsPerMultiProcessor, device) != cudaSuccess) {
+    g_last_cuda_error = static_cast<int>(cudaGetLastError());
+    return LP_ERR_CUDA;
+  }
+  int64_t g = (numel + 255) / 256;
+  const int64_t cap = int64_t(sms) * (tpsm / 256);
+  if (g > cap) g = cap;
+  if (grid) *grid = g;
+  if (inc) *inc = (uint64_t)(((numel - 1) / (256 * g * 4) + 1) * 4);
+  return LP_OK;
+}
+
+template <int N, int kRng>
+int launch_substep_vec(const SubstepArgs& a, bool first, bool next, cudaStream_t s) {
+  const unsigned grid = blocks_for((a.g.total + N - 1) / N);
+  if (first && next) substep_kernel<N, kRng, true, true><<<grid, kBlock, 0, s>>>(a);
+  else if (first) substep_kernel<N, kRng, true, false><<<grid, kBlock, 0, s>>>(a);
+  else if (next) substep_kernel<N, kRng, false, true><<<grid, kBlock, 0, s>>>(a);
+  else substep_kernel<N, kRng, false, false><<<grid, kBlock, 0, s>>>(a);
+  return check_launch();
+}
+
+}  // namespace lp
+
+// ============================================================================
+// C ABI
+// ============================================================================
+using namespace lp;
+
+extern "C" int lp_abi_version(void) { return LP_ABI_VERSION; }
+
+extern "C" const char* lp_status_string(int status) {
+  switch (status) {
+    case LP_OK: return "ok";
+    case LP_ERR_INVALID: return "invalid argument";
+    case LP_ERR_ALIGNMENT: return "misaligned pointer";
+    case LP_ERR_CUDA: return "CUDA launch failed (see lp_last_cuda_error)";
+    case LP_ERR_UNSUPPORTED: return "unsupported size (>= 2^31 elements)";
+    default: return "unknown status";
+  }
+}
+
+extern "C" int lp_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" int lp_torch_randn_geometry(int64_t numel, int device, int64_t* grid_out, uint64_t* increment_out) {
+  return torch_grid(numel, device, grid_out, increment_out);
+}
+
+extern "C" int lp_pack_mask_f32(const float* mask_f32, uint8_t* mask_u8, int64_t n, int invert,
+                                lp_stream_t stream) {
+  if (!mask_f32 || !mask_u8 || n < 0) return LP_ERR_INVALID;
+  if (n >= (int64_t(1) << 31)) return LP_ERR_UNSUPPORTED;
+  if (n == 0) return LP_OK;
+  pack_mask_kernel<<<blocks_for((uint32_t)n), kBlock, 0, (cudaStream_t)stream>>>(mask_f32, mask_u8,
+                                                                                 (uint32_t)n, invert);
+  return check_launch();
+}
+
+extern "C" int lp_prologue_f32(const float* x, const float* y, const float* noise, const uint8_t* mask,
+                               float* x_model, float* x_copy, const float* table, const lp_dims* dims,
+                               lp_stream_t stream) {
+  if (!x || !y || !noise || !mask || !x_model || !table) return LP_ERR_INVALID;
+  Geometry g;
+  if (int rc = make_geometry(dims, g)) return rc;
+  if (g.total == 0) return LP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool v4 = geometry_vec4(g, mask) && aligned16(x) && aligned16(y) && aligned16(noise) &&
+                  aligned16(x_model) && (!x_copy || aligned16(x_copy));
+  if (v4) prologue_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(x, y, noise, mask, x_model, x_copy, table, g);
+  else prologue_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(x, y, noise, mask, x_model, x_copy, table, g);
+  return check_launch();
+}
+
+extern "C" int lp_substep_f32(float* x_model, const float* x0, const float* x0_big, const float* y,
+                              const uint8_t* mask, float* c_state, float* x_copy, float* x0e_out,
+                              const float* table, const lp_dims* dims, const lp_rng* rng, int flags,
+                              lp_stream_t stream) {
+  if (!x_model || !x0 || !y || !mask || !table || !rng) return LP_ERR_INVALID;
+  if (flags & ~(LP_SUBSTEP_FIRST | LP_SUBSTEP_FUSE_NEXT | LP_SUBSTEP_STORE_C)) return LP_ERR_INVALID;
+  const int first = (flags & LP_SUBSTEP_FIRST) != 0;
+  const int has_next = (flags & LP_SUBSTEP_FUSE_NEXT) != 0;
+  if (!x0_big) x0_big = x0;
+  if ((!first || has_next || (flags & LP_SUBSTEP_STORE_C)) && !c_state) return LP_ERR_INVALID;
+  SubstepArgs a;
+  if (int rc = make_geometry(dims, a.g)) return rc;
+  if (a.g.total == 0) return LP_OK;
+  a.x = x_model; a.x0 = x0; a.x0b = x0_big; a.y = y; a.mask = mask; a.c = c_state;
+  a.x_copy = x_copy; a.x0e = x0e_out; a.table = table;
+  a.tape0 = rng->tape0; a.tape1 = rng->tape1; a.rng_state = rng->state;
+  a.seed = rng->seed; a.draw0 = rng->draw0; a.draw1 = rng->draw1; a.torch_T = 0;
+  a.store_c = (flags & LP_SUBSTEP_STORE_C) != 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool f = first != 0, n = has_next != 0;
+
+  if (rng->mode == LP_RNG_TORCH) {
+    int64_t grid = 0;
+    if (int rc = torch_grid(a.g.total, -1, &grid, nullptr)) return rc;
+    a.torch_T = (uint32_t)(grid * 256);
+    const unsigned gb = (unsigned)grid;
+    if (f && n) substep_torch_kernel<true, true><<<gb, kBlock, 0, s>>>(a);
+    else if (f) substep_torch_kernel<true, false><<<gb, kBlock, 0, s>>>(a);
+    else if (n) substep_torch_kernel<false, true><<<gb, kBlock, 0, s>>>(a);
+    else substep_torch_kernel<false, false><<<gb, kBlock, 0, s>>>(a);
+    return check_launch();
+  }
+
+  bool v4 = geometry_vec4(a.g, mask) && aligned16(x_model) && aligned16(x0) && aligned16(x0_big) &&
+            aligned16(y) && (!c_state || aligned16(c_state)) && (!x_copy || aligned16(x_copy)) &&
+            (!x0e_out || aligned16(x0e_out));
+  if (rng->mode == LP_RNG_TAPE) {
+    if (!rng->tape0 || (n && !rng->tape1)) return LP_ERR_INVALID;
+    v4 = v4 && aligned16(rng->tape0) && (!n || aligned16(rng->tape1));
+    return v4 ? launch_substep_vec<4, LP_RNG_TAPE>(a, f, n, s) : launch_substep_vec<1, LP_RNG_TAPE>(a, f, n, s);
+  }
+  if (rng->mode == LP_RNG_PHILOX) {
+    return v4 ? launch_substep_vec<4, LP_RNG_PHILOX>(a, f, n, s) : launch_substep_vec<1, LP_RNG_PHILOX>(a, f, n, s);
+  }
+  return LP_ERR_INVALID;
+}
+
+extern "C" int lp_advance_f32(float* x_model, const float* c_state, const uint8_t* mask, const float* table,
+                              const lp_dims* dims, const lp_rng* rng, int half, lp_stream_t stream) {
+  if (!x_model || !c_state || !mask || !table || !rng) return LP_ERR_INVALID;
+  AdvanceArgs a;
+  if (int rc = make_geometry(dims, a.g)) return rc;
+  if (a.g.total == 0) return LP_OK;
+  a.x = x_model; a.c = c_state; a.mask = mask; a.table = table; a.tape0 = rng->tape0;
+  a.rng_state = rng->state; a.seed = rng->seed; a.draw0 = rng->draw0; a.torch_T = 0; a.half = half != 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rng->mode == LP_RNG_TORCH) {
+    int64_t grid = 0;
+    if (int rc = torch_grid(a.g.total, -1, &grid, nullptr)) return rc;
+    a.torch_T = (uint32_t)(grid * 256);
+    advance_torch_kernel<<<(unsigned)grid, kBlock, 0, s>>>(a);
+  } else if (rng->mode == LP_RNG_TAPE) {
+    if (!rng->tape0) return LP_ERR_INVALID;
+    advance_kernel<LP_RNG_TAPE><<<blocks_for(a.g.total), kBlock, 0, s>>>(a);
+  } else if (rng->mode == LP_RNG_PHILOX) {
+    advance_kernel<LP_RNG_PHILOX><<<blocks_for(a.g.total), kBlock, 0, s>>>(a);
+  } else {
+    return LP_ERR_INVALID;
+  }
+  return check_launch();
+}
+
+extern "C" int lp_epilogue_f32(const float* model_out, const float* y, const uint8_t* mask, float* out,
+                               const lp_dims* dims, lp_stream_t stream) {
+  if (!model_out || !y || !mask || !out) return LP_ERR_INVALID;
+  Geometry g;
+  if (int rc = make_geometry(dims, g)) return rc;
+  if (g.total == 0) return LP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool v4 = geometry_vec4(g, mask) && aligned16(model_out) && aligned16(y) && aligned16(out);
+  if (v4) epilogue_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(model_out, y, mask, out, g);
+  else epilogue_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(model_out, y, mask, out, g);
+  return check_launch();
+}
+
+extern "C" int lp_fill_normal_f32(float* out, int64_t n, const lp_rng* rng, lp_stream_t stream) {
+  if (!out || !rng || n < 0) return LP_ERR_INVALID;
+  if (n >= (int64_t(1) << 31)) return LP_ERR_UNSUPPORTED;
+  if (n == 0) return LP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rng->mode == LP_RNG_PHILOX) {
+    fill_normal_philox_kernel<<<blocks_for((uint32_t)n), kBlock, 0, s>>>(out, (uint32_t)n, rng->seed,
+                                                                        rng->draw0, rng->state);
+    return check_launch();
+  }
+  if (rng->mode == LP_RNG_TORCH) {
+    int64_t grid = 0;
+    if (int rc = torch_grid(n, -1, &grid, nullptr)) return rc;
+    fill_normal_torch_kernel<<<(unsigned)grid, kBlock, 0, s>>>(out, (uint32_t)n, rng->seed, rng->draw0,
+                                                              rng->state, (uint32_t)(grid * 256));
+    return check_launch();
+  }
+  return LP_ERR_INVALID;
+}
+
+extern "C" int lp_synth_denoiser_f32(const float* x, float* h0, float* h1, int64_t n, const float* coef,
+                                     lp_stream_t stream) {
+  if (!x || !h0 || !coef || n < 0) return LP_ERR_INVALID;
+  if (n >= (int64_t(1) << 31)) return LP_ERR_UNSUPPORTED;
+  if (n == 0) return LP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool v4 = n % 4 == 0 && aligned16(x) && aligned16(h0) && (!h1 || aligned16(h1));
+  if (v4)
+    synth_denoiser_kernel<4><<<blocks_for((uint32_t)n / 4), kBlock, 0, s>>>(x, h0, h1, (uint32_t)n, coef[0],
+                                                                          coef[1], coef[2], coef[3], coef[4]);
+  else
+    synth_denoiser_kernel<1><<<blocks_for((uint32_t)n), kBlock, 0, s>>>(x, h0, h1, (uint32_t)n, coef[0], coef[1],
+                                                                      coef[2], coef[3], coef[4]);
+  return check_launch();
+}
+
+extern "C" int lp_l2_flush(void* scratch, size_t bytes, lp_stream_t stream) {
+  if (!scratch) return LP_ERR_INVALID;
+  if (cudaMemsetAsync(scratch, 0, bytes, (cudaStream_t)stream) != cudaSuccess) return check_launch() ? LP_ERR_CUDA : LP_ERR_CUDA;
+  return LP_OK;
+}

@@ -1,0 +1,87 @@
+// Host-side coefficient table for the fused Langevin kernels.
+//
+// Replaces, for one outer diffusion step, the per-sub-step scalar-tensor work of
+// the reference: LanPaint.prepare_step_size (src/LanPaint/lanpaint.py:295-328),
+// the step-size pin (lanpaint.py:81), the A/D/dt mask blend (lanpaint.py:212-214)
+// and the exp/expm1/where/sqrt/clamp of advance_time_overdamped
+// (lanpaint.py:241-251).  Because A and dt take exactly one value per
+// (sample, mask class), all of it collapses into LP_TABLE_STRIDE floats per row,
+// computed here once in fp64 and rounded once to fp32.
+#include <cmath>
+#include <cstdint>
+
+#include "lanpaint_b200.h"
+
+namespace {
+
+struct Advance {
+  double e, k, sd;
+};
+
+// One exact Ornstein-Uhlenbeck advance over h for dx = (-A x + C) dt + sqrt(2) dW
+// (lanpaint.py:241-251, D = sqrt(2) from lanpaint.py:326-327).
+Advance ou_coefficients(double A, double h) {
+  Advance a;
+  const double Ah = A * h;
+  a.e = std::exp(-Ah);
+  const bool tiny = std::fabs(A) < 1e-8;
+  a.k = tiny ? h : (-std::expm1(-Ah)) / A;
+  const double k2 = tiny ? h : (-std::expm1(-2.0 * Ah)) / (2.0 * A);
+  const double var = 2.0 * k2;
+  a.sd = std::sqrt(var > 0.0 ? var : 0.0);
+  return a;
+}
+
+void fill_class(float* c, double A, double g, double dt) {
+  const Advance full = ou_coefficients(A, dt);
+  const Advance half = ou_coefficients(A, 0.5 * dt);
+  c[LP_C_G] = static_cast<float>(g);
+  c[LP_C_DT] = static_cast<float>(dt);
+  c[LP_C_EF] = static_cast<float>(full.e);
+  c[LP_C_KF] = static_cast<float>(full.k);
+  c[LP_C_SF] = static_cast<float>(full.sd);
+  c[LP_C_EH] = static_cast<float>(half.e);
+  c[LP_C_KH] = static_cast<float>(half.k);
+  c[LP_C_SH] = static_cast<float>(half.sd);
+}
+
+}  // namespace
+
+extern "C" int lp_build_coef_table(const double* abt, const double* ve_sigma, const double* rep_noise,
+                                   const double* rep_y, const double* corr, int64_t n_rows,
+                                   const lp_hyper* hp, float* table_out) {
+  if (!abt || !ve_sigma || !hp || !table_out || n_rows < 0) return LP_ERR_INVALID;
+  for (int64_t r = 0; r < n_rows; ++r) {
+    float* t = table_out + r * LP_TABLE_STRIDE;
+    const double a = abt[r];
+    const double one_m = 1.0 - a;
+    // lanpaint.py:81  step_size = StepSize * clamp(1 - abt, min=MinStepFrac)
+    const double h = hp->step_size * (one_m < hp->min_step_frac ? hp->min_step_frac : one_m);
+    // lanpaint.py:301-302,185-190: dtx/2 = h * sigma_x (=1), dty/2 = h * sigma_y (=Beta)
+    const double dt_free = h;
+    const double dt_known = h * hp->beta;
+    // lanpaint.py:313-318: A_x = 1/(1-abt), A_y = (1+Lambda)/(1-abt)
+    const double inv1m = 1.0 / one_m;
+    const double A_free = inv1m;
+    const double A_known = (1.0 + hp->lam) * inv1m;
+    // Coef_C (lanpaint.py:217-220): C = (sqrt(abt) x0e - x_t)/(1-abt) + A x_t
+    //                                 = c_tgt * x0e + (A - 1/(1-abt)) * x_t
+    t[LP_T_CTGT] = static_cast<float>(std::sqrt(a) * inv1m);
+    double S;
+    if (hp->flow) {
+      S = 1.0 / (std::sqrt(a) + std::sqrt(one_m));  // lanpaint.py:97,146,163
+    } else {
+      S = std::sqrt(1.0 + ve_sigma[r] * ve_sigma[r]);  // lanpaint.py:99,148,168
+    }
+    t[LP_T_S] = static_cast<float>(S);
+    t[LP_T_INVS] = static_cast<float>(1.0 / S);
+    t[LP_T_LAM] = static_cast<float>(hp->lam);
+    t[LP_T_ONEPLAM] = static_cast<float>(1.0 + hp->lam);
+    t[LP_T_REPN] = static_cast<float>(rep_noise ? rep_noise[r] : 0.0);
+    t[LP_T_REPY] = static_cast<float>(rep_y ? rep_y[r] : 1.0);
+    t[LP_T_CORR] = static_cast<float>(corr ? corr[r] : 1.0);
+    fill_class(t + LP_T_CLS0, A_free, 0.0, dt_free);
+    fill_class(t + LP_T_CLS1, A_known, hp->lam * inv1m, dt_known);
+  }
+  return LP_OK;
+}

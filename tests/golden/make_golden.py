@@ -1,0 +1,132 @@
+"""Generate golden vectors from the REAL reference engine (run in the build container only).
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference (`/root/reference/src/LanPaint/lanpaint.py`, imported unmodified)
+is driven with stand-in denoisers that follow its own test doubles' protocol
+(tests/test_av_schedule.py:110-130) and with `torch.randn_like` patched to a
+recorded noise tape, so every fixture carries: the inputs, the tape, the
+returned `out`, and the in-place-rewritten `x`.  `/root/reference` does not
+exist on the GPU box, so nothing but this script reads it.
+
+Fixture format (npz): x, y, noise, sigma, mask, ve, abt, flow_t, tape[k,...],
+out, x_new, meta (json string: hyper-parameters, model kind, n_steps, flags).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+from unittest import mock
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from oracle import langevin_oracle as O  # noqa: E402
+from src.LanPaint.lanpaint import LanPaint as RefEngine  # noqa: E402
+
+
+def make_model(kind: str, flow: bool):
+    sampling = O.FlowSampling() if flow else O.VESampling()
+    if kind == "identity":
+        return O.IdentityDenoiser(sampling)
+    if kind == "two_heads":
+        return O.PointwiseDenoiser(sampling)
+    if kind == "bare":
+        return O.PointwiseDenoiser(sampling, heads=0)
+    if kind == "one_tuple":
+        return O.PointwiseDenoiser(sampling, heads=1)
+    raise KeyError(kind)
+
+
+CASES = [
+    # name, shape, flow, model, n_steps, sigma, density(known fraction), lam, beta, step, min_frac, zero_noise
+    dict(name="cfg1_ve_identity_n5", shape=(1, 4, 64, 64), flow=False, model="identity", n=5, sigma=[2.0], dens=0.5),
+    dict(name="ve_two_heads_n5", shape=(1, 4, 16, 16), flow=False, model="two_heads", n=5, sigma=[2.0], dens=0.5),
+    dict(name="ve_two_heads_n1", shape=(1, 4, 16, 16), flow=False, model="two_heads", n=1, sigma=[7.5], dens=0.5),
+    dict(name="ve_two_heads_n2", shape=(1, 4, 16, 16), flow=False, model="two_heads", n=2, sigma=[0.3], dens=0.3),
+    dict(name="ve_two_heads_n0", shape=(1, 4, 16, 16), flow=False, model="two_heads", n=0, sigma=[1.0], dens=0.5),
+    dict(name="ve_two_heads_n10_lowsigma", shape=(1, 4, 16, 16), flow=False, model="two_heads", n=10, sigma=[0.05], dens=0.5),
+    dict(name="ve_bare_n3", shape=(1, 4, 16, 16), flow=False, model="bare", n=3, sigma=[14.6146], dens=0.5),
+    dict(name="ve_one_tuple_n3", shape=(1, 4, 16, 16), flow=False, model="one_tuple", n=3, sigma=[1.3], dens=0.9),
+    dict(name="ve_mask_all_known", shape=(1, 4, 16, 16), flow=False, model="two_heads", n=3, sigma=[2.0], dens=1.0),
+    dict(name="ve_mask_none_known", shape=(1, 4, 16, 16), flow=False, model="two_heads", n=3, sigma=[2.0], dens=0.0),
+    dict(name="ve_engine_default_minfrac0", shape=(1, 4, 16, 16), flow=False, model="two_heads", n=4, sigma=[0.8], dens=0.5, min_frac=0.0),
+    dict(name="ve_hyper_variants", shape=(1, 4, 16, 16), flow=False, model="two_heads", n=4, sigma=[3.0], dens=0.5, lam=8.0, beta=1.5, step=0.15, min_frac=0.4),
+    dict(name="ve_zero_noise_regen", shape=(1, 4, 16, 16), flow=False, model="two_heads", n=2, sigma=[2.0], dens=0.5, zero_noise=True),
+    dict(name="ve_batch2_flowform_replace", shape=(2, 4, 16, 16), flow=False, model="two_heads", n=3, sigma=[2.0, 2.0], dens=0.5),
+    dict(name="ve_batch3_mixed_sigma", shape=(3, 4, 8, 8), flow=False, model="two_heads", n=3, sigma=[0.4, 2.0, 9.0], dens=0.5),
+    dict(name="flow_two_heads_n5", shape=(1, 16, 8, 8), flow=True, model="two_heads", n=5, sigma=[0.6], dens=0.5),
+    dict(name="flow_identity_n3_high_t", shape=(1, 16, 8, 8), flow=True, model="identity", n=3, sigma=[0.97], dens=0.5),
+    dict(name="flow_batch2", shape=(2, 16, 8, 8), flow=True, model="two_heads", n=3, sigma=[0.5, 0.5], dens=0.2),
+    dict(name="video5d_flow_n3", shape=(1, 16, 3, 6, 5), flow=True, model="two_heads", n=3, sigma=[0.7], dens=0.5),
+    dict(name="odd_size_ve_n3", shape=(1, 3, 5, 7), flow=False, model="two_heads", n=3, sigma=[1.1], dens=0.5),
+]
+
+
+def run_case(c: dict, seed: int = 0):
+    g = torch.Generator().manual_seed(seed + hash(c["name"]) % 1000)
+    shape = tuple(c["shape"])
+    flow = c["flow"]
+    x = torch.randn(shape, generator=g)
+    y = torch.randn(shape, generator=g)
+    noise = torch.zeros(shape) if c.get("zero_noise") else torch.randn(shape, generator=g)
+    mshape = (shape[0], 1) + shape[2:]
+    dens = c["dens"]
+    if dens >= 1.0:
+        mask = torch.ones(mshape)
+    elif dens <= 0.0:
+        mask = torch.zeros(mshape)
+    else:
+        mask = (torch.rand(mshape, generator=g) < dens).float()
+    mask = mask.expand(shape).contiguous()
+    sigma = torch.tensor(c["sigma"], dtype=torch.float32)
+    times = O.times_from_sigma(sigma, flow)
+    hp = O.Hyper(n_steps=c["n"], lam=c.get("lam", 5.0), beta=c.get("beta", 1.0),
+                 step_size=c.get("step", 0.2), min_step_frac=c.get("min_frac", 1.0), flow=flow)
+
+    # ---- the real reference, noise drawn through a recording tape ----
+    tape = O.NoiseTape(generator=torch.Generator().manual_seed(1234 + seed))
+    model = make_model(c["model"], flow)
+    eng = RefEngine(model, NSteps=hp.n_steps, Friction=hp.friction, Lambda=hp.lam, Beta=hp.beta,
+                    StepSize=hp.step_size, IS_FLUX=False, IS_FLOW=flow, MinStepFrac=hp.min_step_frac)
+    x_ref = x.clone()
+    with mock.patch.object(torch, "randn_like", tape):
+        out_ref = eng(x_ref, y, noise, sigma, mask, tuple(times), model_options={}, seed=0, n_steps=c["n"])
+    draws = tape.recorded
+
+    # ---- the oracle on the same tape must agree bit for bit ----
+    replay = O.NoiseTape(draws)
+    out_o, x_o = O.outer_step(make_model(c["model"], flow), x.clone(), y, noise, sigma, mask, times, hp,
+                              n_steps=c["n"], draw=replay)
+    assert replay.pos == len(draws), (replay.pos, len(draws))
+    exact = torch.equal(out_o, out_ref) and torch.equal(x_o, x_ref)
+    err = max(float((out_o - out_ref).abs().max()), float((x_o - x_ref).abs().max()))
+    print(f"{c['name']:36s} draws={len(draws):2d} oracle==reference: {exact} (max abs diff {err:.2e})")
+    assert err < 1e-6, c["name"]
+
+    meta = dict(name=c["name"], flow=flow, model=c["model"], n_steps=c["n"], lam=hp.lam, beta=hp.beta,
+                step_size=hp.step_size, min_step_frac=hp.min_step_frac, friction=hp.friction,
+                n_draws=len(draws), oracle_bit_exact=bool(exact), generator="reference@/root/reference lanpaint.py")
+    tape_arr = np.stack([d.numpy() for d in draws]) if draws else np.zeros((0,) + shape, np.float32)
+    np.savez_compressed(
+        os.path.join(HERE, c["name"] + ".npz"),
+        x=x.numpy(), y=y.numpy(), noise=noise.numpy(), sigma=sigma.numpy(),
+        mask=mask[:, :1].numpy().astype(np.uint8), ve=times.ve_sigma.numpy(), abt=times.abt.numpy(),
+        flow_t=times.flow_t.numpy(), tape=tape_arr, out=out_ref.numpy(), x_new=x_ref.numpy(),
+        meta=np.array(json.dumps(meta)))
+
+
+def main():
+    torch.set_num_threads(1)
+    for c in CASES:
+        run_case(c)
+
+
+if __name__ == "__main__":
+    main()

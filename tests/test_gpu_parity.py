@@ -1,0 +1,362 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference's own
+outputs (golden fixtures) and against the oracle on identical inputs.
+
+Tolerances.  BASELINE.json's bar is 1e-3 relative fp32 on the final latent.
+The kernels agree with the reference to fp32 round-off, so the tests assert a
+much tighter engineering bound (TIGHT) and keep the contractual bound as a
+named constant for the record.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden
+from _support import make_model, max_rel, rel_l2, synth_inputs
+from oracle import langevin_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CONTRACT = 1e-3  # north_star tolerance
+TIGHT = 2e-5     # what fp32 round-off between two orderings of the same math allows
+
+
+def _engine(model, meta=None, **kw):
+    from lanpaint_b200.engine import LanPaint
+    meta = meta or {}
+    return LanPaint(model, NSteps=meta.get("n_steps", 5), Friction=meta.get("friction", 15.0),
+                    Lambda=meta.get("lam", 5.0), Beta=meta.get("beta", 1.0), StepSize=meta.get("step_size", 0.2),
+                    IS_FLUX=False, IS_FLOW=meta.get("flow", False), MinStepFrac=meta.get("min_step_frac", 1.0), **kw)
+
+
+def _hyper(meta):
+    return O.Hyper(n_steps=meta["n_steps"], lam=meta["lam"], beta=meta["beta"], step_size=meta["step_size"],
+                   min_step_frac=meta["min_step_frac"], flow=meta["flow"])
+
+
+# ----------------------------------------------------------------------------
+# 1. against the reference's own outputs (fixtures generated from /root/reference)
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_engine_matches_reference_golden(name, cuda_device):
+    from lanpaint_b200.engine import NoiseTape
+    g = load_golden(name)
+    meta = g["meta"]
+    dev = cuda_device
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    x, y, noise, mask = t(g["x"]), t(g["y"]), t(g["noise"]), t(g["mask_full"])
+    sigma = t(g["sigma"])
+    times = (t(g["ve"]), t(g["abt"]), t(g["flow_t"]))
+    tape = NoiseTape([t(d) for d in g["tape"]])
+    model = make_model(meta["model"], meta["flow"])
+    eng = _engine(model, meta, rng=tape)
+    out = eng(x, y, noise, sigma, mask, times, {}, 0, n_steps=meta["n_steps"])
+    torch.cuda.synchronize()
+    assert tape.pos == meta["n_draws"], "draw count/order differs from the reference"
+    e_out = max_rel(out, torch.from_numpy(g["out"]))
+    e_x = max_rel(x, torch.from_numpy(g["x_new"]))  # x is rewritten in place (lanpaint.py:156)
+    assert e_out <= TIGHT and e_x <= TIGHT, (name, e_out, e_x)
+    assert max(e_out, e_x) <= CONTRACT
+    assert model.calls == meta["n_steps"] + 1
+
+
+# ----------------------------------------------------------------------------
+# 2. same seed on the GPU: torch's global CUDA generator, reference draw order
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,flow,n,sigma", [
+    ((1, 4, 64, 64), False, 5, [2.0]),          # BASELINE config 1
+    ((1, 4, 128, 128), False, 5, [7.0]),        # config 2 shape
+    ((2, 4, 32, 32), False, 3, [1.0, 1.0]),     # batch -> flow-form replace quirk
+    ((1, 16, 32, 32), True, 4, [0.6]),          # flow
+    ((1, 16, 21, 80, 45), True, 2, [0.8]),      # Wan-sized 5-D latent: > one torch randn wave
+    ((1, 3, 5, 7), False, 3, [1.5]),            # odd sizes -> scalar path
+])
+def test_same_seed_matches_oracle_on_gpu(shape, flow, n, sigma, cuda_device):
+    dev = cuda_device
+    x, y, noise, m = synth_inputs(shape, seed=3, device=dev)
+    mask = m.expand(shape).contiguous()
+    sig = torch.tensor(sigma, device=dev)
+    times = O.times_from_sigma(sig, flow)
+    hp = O.Hyper(n_steps=n, min_step_frac=1.0, flow=flow)
+    torch.manual_seed(1234)
+    out_o, x_o = O.outer_step(make_model("two_heads", flow), x.clone(), y, noise, sig, mask, times, hp, n_steps=n)
+    off_o = torch.cuda.default_generators[dev.index].get_offset()
+
+    torch.manual_seed(1234)
+    eng = _engine(make_model("two_heads", flow), dict(n_steps=n, flow=flow), rng="torch")
+    xe = x.clone()
+    out_e = eng(xe, y, noise, sig, mask, tuple(times), {}, 0, n_steps=n)
+    off_e = torch.cuda.default_generators[dev.index].get_offset()
+    assert off_e == off_o, "generator must advance exactly as the reference's randn_like calls do"
+    assert max_rel(out_e, out_o) <= TIGHT and max_rel(xe, x_o) <= TIGHT, (max_rel(out_e, out_o), max_rel(xe, x_o))
+
+
+@pytest.mark.parametrize("n", [1, 255, 256, 4097, 303104, 303105, 1209600, 2097152 + 3])
+def test_torch_stream_is_bit_exact(n, cuda_device):
+    """lp_fill_normal_f32(LP_RNG_TORCH) == torch.randn on the same (seed, offset)."""
+    from lanpaint_b200 import _native
+    lib = _native.load()
+    dev = cuda_device
+    gen = torch.cuda.default_generators[dev.index]
+    torch.manual_seed(77)
+    _ = torch.randn(5, device=dev)  # move the offset off zero
+    seed, off = gen.initial_seed(), gen.get_offset()
+    ref = torch.randn(n, device=dev)
+    out = torch.empty(n, device=dev)
+    r = _native.Rng(mode=_native.RNG_TORCH, seed=seed, draw0=off)
+    rc = lib.lp_fill_normal_f32(C.c_void_p(out.data_ptr()), n, C.byref(r),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    g, inc = C.c_int64(0), C.c_uint64(0)
+    assert lib.lp_torch_randn_geometry(n, dev.index, C.byref(g), C.byref(inc)) == 0
+    assert gen.get_offset() - off == inc.value
+    same = torch.equal(out, ref)
+    if not same:  # a libdevice logf difference between toolkits would show up here as 1-ulp noise
+        assert (out - ref).abs().max().item() <= 1e-6, (out - ref).abs().max().item()
+    assert same
+
+
+def test_philox_stream_statistics_and_determinism(cuda_device):
+    from lanpaint_b200 import _native
+    lib = _native.load()
+    dev = cuda_device
+    n = 1 << 22
+    s = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    a, b, c = (torch.empty(n, device=dev) for _ in range(3))
+    for buf, draw in ((a, 0), (b, 1), (c, 0)):
+        r = _native.Rng(mode=_native.RNG_PHILOX, seed=99, draw0=draw)
+        assert lib.lp_fill_normal_f32(C.c_void_p(buf.data_ptr()), n, C.byref(r), s) == 0
+    assert torch.equal(a, c)
+    assert abs(a.mean().item()) < 3e-3 and abs(a.var().item() - 1.0) < 5e-3
+    assert abs((a * b).mean().item()) < 3e-3          # draws are independent
+    assert abs((a[1:] * a[:-1]).mean().item()) < 3e-3  # neighbours are independent
+    assert abs((a ** 4).mean().item() - 3.0) < 0.05    # Gaussian kurtosis
+    assert a.abs().max().item() < 7.0
+
+
+# ----------------------------------------------------------------------------
+# 3. BASELINE sizes: direct parity against the oracle run on the GPU + properties
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,flow,n", [
+    ((8, 4, 128, 128), False, 5),      # north_star "batch 8" target shape
+    ((32, 4, 128, 128), False, 10),    # config 3 unsharded
+    ((1, 16, 128, 128), True, 5),      # config 4 at the ComfyUI boundary
+    ((1, 16, 21, 80, 45), True, 5),    # config 5
+])
+def test_full_size_tape_parity_and_properties(shape, flow, n, cuda_device):
+    from lanpaint_b200.engine import NoiseTape
+    dev = cuda_device
+    x, y, noise, m = synth_inputs(shape, seed=11, device=dev)
+    mask = m.expand(shape).contiguous()
+    B = shape[0]
+    sig = torch.full((B,), 0.7 if flow else 2.5, device=dev)
+    times = O.times_from_sigma(sig, flow)
+    hp = O.Hyper(n_steps=n, min_step_frac=1.0, flow=flow)
+    tape = O.NoiseTape(generator=torch.Generator().manual_seed(5))
+    out_o, x_o = O.outer_step(make_model("two_heads", flow), x.clone(), y, noise, sig, mask, times, hp,
+                              n_steps=n, draw=tape)
+    eng = _engine(make_model("two_heads", flow), dict(n_steps=n, flow=flow), rng=NoiseTape(tape.recorded))
+    xe = x.clone()
+    out_e = eng(xe, y, noise, sig, m, tuple(times), {}, 0, n_steps=n)  # [B,1,...] mask: 1/C byte per element path
+    assert max_rel(out_e, out_o) <= TIGHT and max_rel(xe, x_o) <= TIGHT
+    assert rel_l2(xe, x_o) <= 1e-6
+    # property: the known region of `out` is exactly the clean latent (lanpaint.py:154)
+    known = mask.bool()
+    assert torch.equal(out_e[known], y[known])
+    # property: one launch per sub-step (+ mask pack, prologue, epilogue)
+    assert eng.launches == n + 3 and eng.model_calls == n + 1
+
+
+def test_batch_equals_independent_requests(cuda_device):
+    """Samples never interact: a batch run == each sample run alone (per_sample replace)."""
+    from lanpaint_b200.engine import NoiseTape
+    dev = cuda_device
+    shape = (4, 4, 32, 32)
+    x, y, noise, m = synth_inputs(shape, seed=5, device=dev)
+    sig = torch.tensor([0.5, 2.0, 6.0, 13.0], device=dev)
+    times = O.times_from_sigma(sig, False)
+    draws = [torch.randn(shape, device=dev) for _ in range(5)]
+    eng = _engine(make_model("two_heads", False), dict(n_steps=3), rng=NoiseTape(draws), batched_replace="per_sample")
+    xb = x.clone()
+    out_b = eng(xb, y, noise, sig, m, tuple(times), {}, 0, n_steps=3)
+    for b in range(4):
+        sl = slice(b, b + 1)
+        e1 = _engine(make_model("two_heads", False), dict(n_steps=3), rng=NoiseTape([d[sl].contiguous() for d in draws]))
+        x1 = x[sl].clone()
+        o1 = e1(x1, y[sl].contiguous(), noise[sl].contiguous(), sig[sl], m[sl].contiguous(),
+                tuple(t[sl] for t in times), {}, 0, n_steps=3)
+        assert torch.equal(o1, out_b[sl]) and torch.equal(x1, xb[sl])
+
+
+def test_vector_and_scalar_paths_agree_bitwise(cuda_device):
+    """A 4-byte-misaligned view forces the scalar kernels; results must equal the 128-bit path."""
+    from lanpaint_b200.engine import NoiseTape
+    dev = cuda_device
+    shape = (2, 4, 16, 16)
+    x, y, noise, m = synth_inputs(shape, seed=9, device=dev)
+    sig = torch.tensor([1.5, 1.5], device=dev)
+    times = O.times_from_sigma(sig, False)
+    draws = [torch.randn(shape, device=dev) for _ in range(5)]
+
+    def run(xin):
+        eng = _engine(make_model("two_heads", False), dict(n_steps=3), rng=NoiseTape(draws))
+        out = eng(xin, y, noise, sig, m, tuple(times), {}, 0, n_steps=3)
+        return out, xin
+
+    o_vec, x_vec = run(x.clone())
+    pad = torch.empty(x.numel() + 1, device=dev)
+    x_mis = pad[1:].view(shape)
+    x_mis.copy_(x)
+    assert x_mis.data_ptr() % 16 != 0
+    o_sc, x_sc = run(x_mis)
+    assert torch.equal(o_vec, o_sc) and torch.equal(x_vec, x_sc)
+
+
+def test_philox_mode_reproducible_and_sane(cuda_device):
+    dev = cuda_device
+    shape = (2, 4, 64, 64)
+    x, y, noise, m = synth_inputs(shape, seed=2, device=dev)
+    sig = torch.tensor([2.0, 2.0], device=dev)
+    times = O.times_from_sigma(sig, False)
+
+    def run(seed):
+        torch.manual_seed(seed)
+        eng = _engine(make_model("two_heads", False), dict(n_steps=4), rng="philox")
+        xx = x.clone()
+        return eng(xx, y, noise, sig, m, tuple(times), {}, 0, n_steps=4), xx
+
+    o1, x1 = run(1)
+    o2, x2 = run(1)
+    o3, x3 = run(2)
+    assert torch.equal(x1, x2) and torch.equal(o1, o2)
+    assert not torch.equal(x1, x3)
+    # distributional sanity against the oracle with its own (different) stream
+    torch.manual_seed(1)
+    _, x_o = O.outer_step(make_model("two_heads", False), x.clone(), y, noise, sig, m.expand(shape), times,
+                          O.Hyper(n_steps=4, min_step_frac=1.0), n_steps=4)
+    free = ~m.expand(shape).bool()
+    assert abs(x1[free].std().item() / x_o[free].std().item() - 1.0) < 0.05
+    assert abs(x1[free].mean().item() - x_o[free].mean().item()) < 0.1
+
+
+# ----------------------------------------------------------------------------
+# 4. edge cases and error behaviour
+# ----------------------------------------------------------------------------
+def test_cpu_tensor_is_rejected_loudly():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    eng = _engine(make_model("identity", False))
+    x = torch.zeros(1, 4, 8, 8)
+    with pytest.raises(RuntimeError):
+        eng(x, x, x, torch.tensor([1.0]), x, (torch.tensor([1.0]),) * 3, {}, 0)
+
+
+def test_empty_model_output_raises_value_error(cuda_device):
+    class Empty(O.PointwiseDenoiser):
+        def __call__(self, x, sigma, model_options=None, seed=None):
+            return ()
+    dev = cuda_device
+    x, y, noise, m = synth_inputs((1, 4, 8, 8), device=dev)
+    sig = torch.tensor([1.0], device=dev)
+    eng = _engine(Empty(O.VESampling()))
+    with pytest.raises(ValueError, match="Model output is empty"):
+        eng(x, y, noise, sig, m, tuple(O.times_from_sigma(sig, False)), {}, 0, n_steps=2)
+
+
+def test_noncontiguous_and_half_inputs(cuda_device):
+    from lanpaint_b200.engine import NoiseTape
+    dev = cuda_device
+    shape = (1, 4, 16, 16)
+    x, y, noise, m = synth_inputs(shape, seed=4, device=dev)
+    sig = torch.tensor([2.0], device=dev)
+    times = O.times_from_sigma(sig, False)
+    draws = [torch.randn(shape, device=dev) for _ in range(3)]
+    ref_eng = _engine(make_model("two_heads", False), dict(n_steps=2), rng=NoiseTape(draws))
+    x_ref = x.clone()
+    o_ref = ref_eng(x_ref, y, noise, sig, m, tuple(times), {}, 0, n_steps=2)
+    # channels-last strided x: the in-place contract must still hold
+    x_nc = x.clone().permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    assert not x_nc.is_contiguous()
+    eng = _engine(make_model("two_heads", False), dict(n_steps=2), rng=NoiseTape(draws))
+    o = eng(x_nc, y, noise, sig, m, tuple(times), {}, 0, n_steps=2)
+    assert torch.equal(o, o_ref) and torch.equal(x_nc, x_ref)
+
+
+def test_flat_3d_latent_and_zero_steps(cuda_device):
+    """[1,1,8] flat pack, n_steps=0: replace + final call only (tests/test_av_schedule.py:204-219 shape)."""
+    dev = cuda_device
+    x = torch.zeros(1, 1, 8, device=dev)
+    y = torch.zeros_like(x)
+    noise = torch.ones_like(x)
+    sig = torch.tensor([0.5], device=dev)
+    mask = torch.ones_like(x)
+    model = make_model("identity", True)
+    eng = _engine(model, dict(n_steps=0, flow=True, lam=1.0))
+    eng(x, y, noise, sig, mask, (torch.tensor([1.0], device=dev), torch.tensor([0.5], device=dev), sig), None, 0,
+        n_steps=0)
+    assert torch.allclose(model.last_input.flatten(), torch.full((8,), 0.5, device=dev))
+    assert model.calls == 1
+
+
+def test_c_abi_rejects_bad_arguments():
+    from lanpaint_b200 import _native
+    lib = _native.load()
+    d = _native.Dims(1, 16, 16, 16, 0)
+    r = _native.Rng(mode=_native.RNG_PHILOX)
+    assert lib.lp_substep_f32(None, None, None, None, None, None, None, None, None, C.byref(d), C.byref(r), 1, None) == 1
+    assert lib.lp_prologue_f32(None, None, None, None, None, None, None, C.byref(d), None) == 1
+    assert lib.lp_status_string(1).decode() == "invalid argument"
+
+
+def test_advance_abi_matches_oracle(cuda_device):
+    """lp_advance_f32 == advance_time_overdamped (lanpaint.py:232-254) on the model-space state."""
+    from lanpaint_b200 import _native
+    from lanpaint_b200.schedule import Hyper, build_table
+    lib = _native.load()
+    dev = cuda_device
+    B, Cc, S = 2, 4, 64
+    torch.manual_seed(0)
+    x = torch.randn(B, Cc, S, device=dev)
+    c = torch.randn_like(x)
+    xi = torch.randn_like(x)
+    mask = (torch.rand(B, 1, S, device=dev) < 0.5)
+    sig = torch.tensor([0.7, 3.0], device=dev)
+    ve, abt, _ = O.times_from_sigma(sig, False)
+    hp = Hyper(0.2, 5.0, 1.0, 1.0, False)
+    tab = torch.from_numpy(build_table(abt.cpu().numpy(), ve.cpu().numpy(), hp)).to(dev)
+    for half in (0, 1):
+        xk = x.clone()
+        d = _native.Dims(B, Cc * S, S, S, 0)
+        r = _native.Rng(mode=_native.RNG_TAPE, tape0=xi.data_ptr())
+        m8 = mask.to(torch.uint8).contiguous()
+        rc = lib.lp_advance_f32(C.c_void_p(xk.data_ptr()), C.c_void_p(c.data_ptr()), C.c_void_p(m8.data_ptr()),
+                                C.c_void_p(tab.data_ptr()), C.byref(d), C.byref(r), half,
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        # oracle in VP space, fp64
+        mf = mask.expand(B, Cc, S).double()
+        abt_b = abt.double().view(B, 1, 1)
+        Sx = (1 + ve.double() ** 2).sqrt().view(B, 1, 1)
+        step = 0.2 * (1 - abt_b).clamp(min=1.0)
+        cf = O.branch_coefficients(abt_b, step, torch.ones_like(abt_b), torch.ones_like(abt_b), 5.0)
+        A = cf.A_x * (1 - mf) + cf.A_y * mf
+        D = cf.D_x * (1 - mf) + cf.D_y * mf
+        dt = cf.half_dt_x * (1 - mf) + cf.half_dt_y * mf
+        h = dt / 2 if half else dt
+        want = O.ou_advance(x.double() / Sx, h, A, c.double(), D, lambda t: xi.double()) * Sx
+        assert max_rel(xk, want) <= TIGHT
+
+
+def test_synth_denoiser_kernel_matches_torch(cuda_device):
+    from lanpaint_b200 import _native
+    lib = _native.load()
+    dev = cuda_device
+    x = torch.randn(3, 4, 33, 31, device=dev)
+    h0, h1 = torch.empty_like(x), torch.empty_like(x)
+    coef = (C.c_float * 5)(0.7, 0.1, 0.0, 0.6, -0.05)
+    rc = lib.lp_synth_denoiser_f32(C.c_void_p(x.data_ptr()), C.c_void_p(h0.data_ptr()), C.c_void_p(h1.data_ptr()),
+                                   x.numel(), coef, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0
+    w0, w1 = make_model("two_heads", False)(x, None)
+    assert max_rel(h0, w0) <= 1e-6 and max_rel(h1, w1) <= 1e-6
