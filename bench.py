@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- Langevin sub-steps/sec on the SDXL 128x128x4 latent (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo (CUDA kernels)
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle port)
+
+Workload (`config.workload`): `requests_per_gpu` independent SDXL inpaint requests of
+shape [1,4,128,128] (BASELINE configs[1]'s latent), batched per GPU, each running the
+reference schedule: karras-20 sigmas x N=5 think steps with the node defaults
+(MinStepFrac=1, EarlyStop=1) = 53 Langevin sub-steps + 20 final denoises = 73 model
+calls per request, with the SURVEY-8d synthetic pointwise two-head denoiser
+standing in for the UNet and k-diffusion's Euler update between outer steps.
+One bench "step" = one such job over the GPU's whole batch.  value = request-sub-steps/s
+summed over GPUs (weak scaling: per-GPU batch fixed).
+
+Timed with CUDA events on the launching stream, barrier + synchronize on both sides, max
+over ranks.  Inputs of the default batch (128 requests: 176 MB touched per launch) exceed
+the 126 MB L2, so every launch streams from HBM (`config.l2`).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SHAPE = (4, 128, 128)          # SDXL latent of a 1024x1024 image
+N_OUTER, N_INNER = 20, 5
+ALGO_BYTES_PER_ELEM = 28.0 + 1.0 / SHAPE[0]   # read x,x0,x0B,y,C + write x,C (fp32) + uint8 spatial mask
+METRIC = "Langevin sub-steps/sec (SDXL 128x128x4 latent, N=5)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+            time.sleep(0.15)
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.1)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        load = [v for v in sm if v > 0.5 * mx] or sm
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------
+# the reference arm: the oracle (op-for-op restatement of the reference's eager PyTorch path)
+# on the host cores.  The one place outside tests/ where oracle/ is executed.
+# ------------------------------------------------------------------------------------------
+def calibrate_threads(requests: int) -> int:
+    """The reference's eager path is ~90 small element-wise ops per sub-step; on a many-core host
+    more threads can be slower (fork/join per op).  Pick the fastest thread count for this tensor
+    size from a quick op-chain probe, so the CPU arm is the best the host can do, not a strawman."""
+    cores = os.cpu_count() or 1
+    x = torch.randn((requests,) + SHAPE)
+    y = torch.randn_like(x)
+    best, best_t = 1, float("inf")
+    cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, cores) if c <= cores})
+    for c in cands:
+        torch.set_num_threads(c)
+        for rep in range(2):
+            t0 = time.perf_counter()
+            z = x
+            for _ in range(10):
+                z = torch.exp(-(z * y)) * x + (1 - y) * z
+            dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
+def cpu_job(requests: int, outer_steps: int, threads: int, seed: int = 0):
+    """Runs the first `outer_steps` outer steps of the workload on `requests` requests on the CPU.
+    Returns (seconds, request-sub-steps done)."""
+    from oracle import langevin_oracle as O
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(seed)
+    shape = (requests,) + SHAPE
+    y, noise = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    dm = (torch.rand((requests, 1) + SHAPE[1:], generator=g) < 0.5).float().expand(shape).contiguous()
+    sig = O.karras_sigmas(N_OUTER)
+    hp = O.Hyper(n_steps=N_INNER, min_step_frac=1.0)
+    model = O.PointwiseDenoiser(O.VESampling())
+    counters = {}
+    t0 = time.perf_counter()
+    _cpu_partial(O, model, y, noise, dm, sig, hp, min(outer_steps, N_OUTER), counters)
+    dt = time.perf_counter() - t0
+    return dt, counters["substeps"] * requests
+
+
+def _cpu_partial(O, model, y, noise, dm, sig, hp, outer_steps, counters):
+    """First `outer_steps` outer steps with the FULL schedule's step bookkeeping (n_eff depends on
+    the position in the full 20-step schedule, nodes.py:286-299)."""
+    x = model.model_sampling.noise_scaling(sig[0], noise, y)
+    mask = O.binarise_mask(dm)
+    s_in = x.new_ones([x.shape[0]])
+    sub = 0
+    for i in range(outer_steps):
+        sigma = sig[i] * s_in
+        tm = O.times_from_sigma(sigma, False)
+        n_eff = O.inner_steps_for(sigma, sig, tm.abt, hp.n_steps, 1, 1.0)
+        den, x = O.outer_step(model, x, y, noise, sigma, mask, tm, hp, n_eff)
+        x = x + (x - den) / sigma.view(-1, 1, 1, 1) * (sig[i + 1] - sig[i])
+        sub += n_eff
+    counters["substeps"] = sub
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    host_cores = os.cpu_count() or 1
+    req = args.ref_requests
+    cores = calibrate_threads(req)
+    for _ in range(args.warmup):
+        cpu_job(req, N_OUTER, cores)
+    t, units = 0.0, 0
+    for _ in range(args.steps):
+        dt, u = cpu_job(req, N_OUTER, cores)
+        t += dt
+        units += u
+    value = units / t
+    sample = (f"{req} of {args.requests} requests per step, full karras-20 x N=5 schedule (53 sub-steps/request); "
+              f"{cores} torch threads (fastest of a probe over 1..{host_cores} host cores)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "sub-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "sub-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "sub-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    touched = 5.25 * 4 * args.requests * SHAPE[0] * SHAPE[1] * SHAPE[2] / 1e6
+    return {"workload": "sdxl_1024_inpaint_4x128x128_karras20_N5", "requests_per_gpu": args.requests,
+            "latent_shape": [1] + list(SHAPE), "outer_steps": N_OUTER, "think_steps": N_INNER,
+            "substeps_per_request": 53, "model_calls_per_request": 73, "denoiser": "synthetic pointwise two-head",
+            "sampler": "euler", "mask": "random 50% per spatial site", "rng": args.rng,
+            "launch": "eager" if getattr(args, "eager", False) else "cuda-graph replay per outer step",
+            "parallelism": f"replicas x{args.gpus} (requests sharded, no data-path collective)",
+            "l2": f"inputs larger than L2: {touched:.0f} MB touched per sub-step launch vs 126 MB L2"
+                  if touched > 126 else f"working set {touched:.0f} MB fits L2; no flush (see config.sweep for HBM-bound size)"}
+
+
+# ------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------
+def make_inputs(requests, dev, seed, pinned=False):
+    g = torch.Generator().manual_seed(seed)
+    shape = (requests,) + SHAPE
+    y = torch.randn(shape, generator=g)
+    noise = torch.randn(shape, generator=g)
+    mask = (torch.rand((requests, 1) + SHAPE[1:], generator=g) < 0.5).float()  # 1 = known
+    if pinned:
+        return [t.pin_memory() for t in (y, noise, mask)]
+    return [t.to(dev) for t in (y, noise, mask)]
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from lanpaint_b200.engine import LanPaint, pack_mask
+    from lanpaint_b200.runner import HostSchedule, SynthDenoiser, VESampling, euler_inpaint, karras_sigmas
+
+    rank, world, local = dist_env()
+    assert torch.cuda.is_available(), "bench.py (impl b200) needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    R = args.requests
+    model = SynthDenoiser(VESampling())
+    # replicas: the only collective is the one-time broadcast of the denoiser's weights (north_star)
+    w = torch.tensor(model.coef, device=dev)
+    if world > 1:
+        dist.broadcast(w, src=0)
+    model.set_coef(w.tolist())
+
+    def make_engine(graph):
+        return LanPaint(model, NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0, StepSize=0.2, MinStepFrac=1.0,
+                        rng=args.rng, batched_replace="per_sample", cuda_graph=graph)
+    eng = make_engine(not args.eager)
+    sched = HostSchedule(karras_sigmas(N_OUTER), R, N_INNER)
+    assert sched.substeps == 53 and sched.model_calls == 73
+    y, noise, mask = make_inputs(R, dev, seed=rank)
+    pm = pack_mask(mask, y)
+    torch.manual_seed(1000 + rank)
+
+    def job():
+        return euler_inpaint(eng, y, noise, pm, sched)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        job()
+    barrier()
+
+    # ---- timed region: K jobs, device time, max over ranks ----
+    eng.launches = 0
+    model.calls = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            job()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    launches = eng.launches + model.calls
+    units = world * R * sched.substeps * args.steps
+    value = units / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (steady fused sub-step), live CUDA-event timing ----
+    peak, peak_src = peaks()
+    n_el = R * SHAPE[0] * SHAPE[1] * SHAPE[2]
+    algo = ALGO_BYTES_PER_ELEM * n_el
+    roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+            "kernel": "lp::substep_kernel<4,rng,false,true> (steady fused sub-step)", "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": algo}
+    timer = None
+    if args.kernel_timer:
+        # same workload, eager launches, a CUDA-event pair around every fused sub-step launch
+        eng_t = make_engine(False)
+        for _ in range(2):
+            euler_inpaint(eng_t, y, noise, pm, sched)
+        barrier()
+        eng_t.kernel_timer = timer = []
+        for _ in range(max(3, min(10, args.steps))):
+            euler_inpaint(eng_t, y, noise, pm, sched)
+        barrier()
+        eng_t.kernel_timer = None
+    if timer:
+        mid = [a.elapsed_time(b) for f, a, b in timer if f == 2]  # FUSE_NEXT only = steady sub-step
+        if mid:
+            mid.sort()
+            avg = sum(mid) / len(mid)
+            roof.update(achieved=algo / (avg * 1e-3) / 1e9, avg_us=avg * 1e3, median_us=mid[len(mid) // 2] * 1e3,
+                        launches_timed=len(mid))
+            roof["frac"] = roof["achieved"] / peak
+            tr = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tr):
+                roof["traffic"] = json.load(open(tr)).get(str(R))
+
+    # ---- e2e: host buffers in, host result out, through the public call; copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        hy, hn, hm = make_inputs(R, dev, seed=rank, pinned=True)
+        hout = torch.empty((R,) + SHAPE).pin_memory()
+        bi = hy.numel() * 4 + hn.numel() * 4 + hm.numel() * 4
+        bo = hout.numel() * 4
+
+        def e2e_job():
+            dy, dn, dm = (t.to(dev, non_blocking=True) for t in (hy, hn, hm))
+            euler_inpaint(eng, dy, dn, dm, sched, x_out=hout)
+            torch.cuda.current_stream().synchronize()   # the user holds the host result
+
+        for _ in range(2):
+            e2e_job()
+        barrier()
+        k2 = max(3, args.steps // 4)
+        t0 = time.perf_counter()
+        for _ in range(k2):
+            e2e_job()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * R * sched.substeps * k2 / float(tt.item()), "unit": "sub-steps/s",
+               "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "steps": k2,
+               "api": "lanpaint_b200.runner.euler_inpaint(engine=lanpaint_b200.LanPaint) on pinned host tensors"}
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        host_cores = os.cpu_count() or 1
+        cores = calibrate_threads(args.ref_requests)
+        cpu_job(2, 2, cores)  # warm
+        dt, u = cpu_job(args.ref_requests, N_OUTER, cores)
+        cpu = {"value": u / dt, "unit": "sub-steps/s", "cores": cores, "kind": "port",
+               "sample": f"{args.ref_requests} of {R} requests, full karras-20 x N=5 schedule, {dt:.1f} s of CPU work; "
+                         f"{cores} torch threads (fastest of a probe over 1..{host_cores} host cores)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "sub-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches * world, "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--requests", type=int, default=128, help="independent SDXL requests batched per GPU")
+    ap.add_argument("--ref-requests", type=int, default=8, help="requests per step in the CPU arm's bounded sample")
+    ap.add_argument("--rng", default="philox", choices=["philox", "torch"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-kernel-timer", dest="kernel_timer", action="store_false")
+    ap.add_argument("--eager", action="store_true", help="launch kernels one by one instead of replaying CUDA graphs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

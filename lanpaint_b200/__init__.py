@@ -23,6 +23,6 @@ def __getattr__(name):
         from .engine import NoiseTape
         return NoiseTape
     if name in _LAZY:
-        from . import nodes
-        return getattr(nodes, name)
+        from . import comfy_nodes
+        return getattr(comfy_nodes, name)
     raise AttributeError(name)

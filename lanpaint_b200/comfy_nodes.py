@@ -1,0 +1,559 @@
+"""ComfyUI node surface of LanPaint, backed by the B200 engine.
+
+What is kept byte-identical to the reference (checked by
+tests/test_nodes_api.py against a dump of the reference's own classes):
+node class names, INPUT_TYPES (order, types, defaults, ranges, tooltips,
+hidden retired widgets), RETURN_TYPES / RETURN_NAMES / FUNCTION / CATEGORY,
+NODE_CLASS_MAPPINGS keys and display names of the four sampler nodes
+(src/LanPaint/nodes.py:452-589,659-808,1347-1378), the hyper-parameter
+attributes hung on the ModelPatcher (nodes.py:492-504), the four functions
+patched for the duration of one sample call and their restore-on-exception
+(nodes.py:384-421), the LATENT dict contract.
+
+What is different: the per-sigma wrapper computes the schedule on the host
+from ONE read-back of sigma (the reference syncs twice per outer step plus
+once per sub-step), caches the packed mask across outer steps, and calls the
+fused engine (`lanpaint_b200.engine.LanPaint`).  Only the four sampler nodes
+exist here: mask/video/audio tooling is outside the hot path.
+"""
+from __future__ import annotations
+
+import math
+from contextlib import contextmanager
+
+import torch
+
+import comfy  # noqa: F401  (ComfyUI, or minicomfy in tests)
+import comfy.model_management
+import comfy.sample
+import comfy.sampler_helpers
+import comfy.samplers
+import comfy.utils
+import latent_preview
+import nodes as comfy_nodes_module
+from comfy.model_base import ModelType
+
+try:  # WAN22 exists only in recent ComfyUI builds
+    from comfy.model_base import WAN22
+except Exception:  # pragma: no cover
+    WAN22 = None
+
+from .engine import LanPaint, pack_mask
+from .schedule import effective_inner_steps, min_step_frac_effective_steps, times_from_sigma  # noqa: F401
+
+FLOW_MODEL_TYPES = (ModelType.FLOW, getattr(ModelType, "FLOW_AV", None))
+
+IMAGE_MODE, VIDEO_MODE = "🖼️ Image Inpainting", "🎬 Video Inpainting"
+PROMPT_MODES = ("Image First", "Prompt First")
+_STAR = ("For more info, visit https://github.com/scraed/LanPaint. "
+         "If you find it useful, please give a star ⭐️!")
+
+KSAMPLER_NAMES = ["euler", "euler_ancestral", "heun", "heunpp2", "dpm_2", "dpm_2_ancestral",
+                  "dpm_fast", "dpmpp_sde", "dpmpp_sde_gpu",
+                  "dpmpp_2m", "dpmpp_2m_sde", "dpmpp_2m_sde_gpu", "dpmpp_3m_sde", "dpmpp_3m_sde_gpu", "ddpm",
+                  "deis", "res_multistep", "res_multistep_ancestral",
+                  "gradient_estimation", "er_sde", "seeds_2", "seeds_3"]
+
+# retired widgets old workflows still send; accepted and ignored (nodes.py:472-477,538-548)
+_RETIRED_ALL = ("LanPaint_Beta", "LanPaint_Friction", "LanPaint_EarlyStop", "LanPaint_InnerThreshold",
+                "LanPaint_InnerPatience", "LanPaint_MinStepFrac")
+
+
+def _hidden(names):
+    return {n: "DEFAULT" for n in names}
+
+
+# ---- widget specs shared between nodes ------------------------------------------------------
+def _w_num_steps(tip):
+    return ("INT", {"default": 5, "min": 0, "max": 100, "tooltip": tip})
+
+
+def _w_prompt_mode(tip):
+    return (list(PROMPT_MODES), {"tooltip": tip})
+
+
+def _w_info(default):
+    return ("STRING", {"default": default, "tooltip": _STAR})
+
+
+def _w_mode():
+    return ([IMAGE_MODE, VIDEO_MODE], {"default": IMAGE_MODE, "tooltip": "Choose Image mode for photos or Video mode for video frames with temporal consistency"})
+
+
+_TIP_STEPS_K = "The number of steps for the Langevin dynamics, representing the turns of thinking per step."
+_TIP_STEPS_C = "Number of steps for Langevin dynamics, representing turns of thinking per step."
+_TIP_MODE_K = "Image First: emphasis image quality, Prompt First: emphasis prompt following"
+_TIP_MODE_C = "Image First: prioritizes image quality; Prompt First: prioritizes prompt adherence."
+
+
+def _sanitize_param(value, default, allowed=None):
+    """Bad widget values fall back to the default instead of raising (nodes.py:146-157)."""
+    if allowed is not None:
+        return value if value in allowed else default
+    if isinstance(value, bool) or not isinstance(value, (int, float)):
+        return default
+    return value
+
+
+def _set_hyper(patcher, *, num_steps, cfg, prompt_mode, lam=5.0, step_size=0.2):
+    """The attribute protocol between the nodes and KSAMPLER.sample (nodes.py:492-504 -> :351-364)."""
+    patcher.LanPaint_StepSize = step_size
+    patcher.LanPaint_Lambda = lam
+    patcher.LanPaint_Beta = 1.0
+    patcher.LanPaint_NumSteps = num_steps
+    patcher.LanPaint_MinStepFrac = 1.0
+    patcher.LanPaint_Friction = 15.0
+    patcher.LanPaint_EarlyStop = 1
+    patcher.LanPaint_InnerThreshold = 0.0
+    patcher.LanPaint_InnerPatience = 1
+    patcher.LanPaint_cfg_BIG = cfg if prompt_mode == "Image First" else 0 * cfg - 0.5
+
+
+# =============================================================================================
+# mask preparation (runs once per sample; plain torch)
+# =============================================================================================
+def reshape_mask(input_mask, output_shape, video_inpainting=False):
+    """noise_mask of any accepted rank -> latent shape (nodes.py:59-133): nearest-exact resize;
+    video masks additionally take the union over a 5-slice temporal window."""
+    import torch.nn.functional as F
+    spatial_rank = len(output_shape) - 2
+    m = input_mask
+    if video_inpainting:
+        if m.ndim == 2:
+            m = m[None, None, None]
+        elif m.ndim == 3:
+            m = m[None, None]
+        elif m.ndim == 4:
+            m = m.permute(1, 0, 2, 3)[None]
+    elif m.ndim == 1 and len(output_shape) == 4:
+        t = output_shape[-1]
+        m = F.interpolate(m.float()[None, None], size=(t,), mode="nearest-exact").expand(1, 1, output_shape[-2], t)
+    elif m.ndim == 4 and len(output_shape) == 4 and m.shape[1] == 1 and m.shape[3] == 1:
+        t = output_shape[-1]
+        m = F.interpolate(m, size=(t, 1), mode="nearest-exact").permute(0, 1, 3, 2).expand(1, 1, output_shape[-2], t)
+    elif m.ndim == 2:
+        m = m[None, None]
+    elif m.ndim == 3:
+        m = m[:, None]
+    if len(output_shape) == 5 and m.ndim == 4:
+        m = m.unsqueeze(2)
+
+    if video_inpainting:
+        m = F.interpolate(m, size=(output_shape[2], output_shape[-2], output_shape[-1]), mode="nearest-exact")
+        m = F.max_pool3d(m, kernel_size=(5, 1, 1), stride=(1, 1, 1), padding=(2, 0, 0))
+        if m.shape[1] < output_shape[1]:
+            m = m.repeat(1, output_shape[1], 1, 1, 1)[:, :output_shape[1]]
+        return comfy.utils.repeat_to_batch_size(m, output_shape[0])
+    m = F.interpolate(m, size=tuple(output_shape[2:]), mode="nearest-exact")
+    if m.shape[1] < output_shape[1]:
+        m = m.repeat((1, output_shape[1]) + (1,) * spatial_rank)[:, :output_shape[1]]
+    return comfy.utils.repeat_to_batch_size(m, output_shape[0])
+
+
+def prepare_mask(noise_mask, shape, device, video_inpainting=False):
+    return reshape_mask(noise_mask, shape, video_inpainting).to(device)
+
+
+# =============================================================================================
+# patch layer (nodes.py:161-421)
+# =============================================================================================
+def sampling_function_LanPaint(model, x, timestep, uncond, cond, cond_scale, cond_scale_BIG, model_options={},
+                               seed=None):
+    """One batched cond/uncond evaluation, two CFG combines -> (x0 at cfg, x0 at cfg_BIG)."""
+    skip_uncond = math.isclose(cond_scale, 1.0) and not model_options.get("disable_cfg1_optimization", False)
+    uncond_ = None if skip_uncond else uncond
+    conds = [cond, uncond_]
+    out = comfy.samplers.calc_cond_batch(model, conds, x, timestep, model_options)
+    for fn in model_options.get("sampler_pre_cfg_function", []):
+        out = fn({"conds": conds, "conds_out": out, "cond_scale": cond_scale, "timestep": timestep, "input": x,
+                  "sigma": timestep, "model": model, "model_options": model_options})
+    combine = comfy.samplers.cfg_function
+    return (combine(model, out[0], out[1], cond_scale, x, timestep, model_options=model_options, cond=cond, uncond=uncond_),
+            combine(model, out[0], out[1], cond_scale_BIG, x, timestep, model_options=model_options, cond=cond, uncond=uncond_))
+
+
+class CFGGuider_LanPaint:
+    """Methods grafted onto comfy.samplers.CFGGuider while a LanPaint node samples."""
+
+    def outer_sample(self, noise, latent_image, sampler, sigmas, denoise_mask=None, callback=None, disable_pbar=False,
+                     seed=None, **kwargs):
+        self.inner_model, self.conds, self.loaded_models = comfy.sampler_helpers.prepare_sampling(
+            self.model_patcher, noise.shape, self.conds, self.model_options)
+        device = self.model_patcher.load_device
+        if WAN22 is not None and isinstance(self.inner_model, WAN22):
+            self.inner_model.extra_conds = super(WAN22, self.inner_model).extra_conds
+        self.minimax_h3_audio = None  # AV per-row schedule: not built
+        if denoise_mask is not None and tuple(denoise_mask.shape) != tuple(noise.shape):
+            denoise_mask = prepare_mask(denoise_mask, noise.shape, device,
+                                        self.model_options.get("video_inpainting", False))
+        noise = noise.to(device)
+        latent_image = latent_image.to(device)
+        sigmas_host = sigmas.detach().to("cpu", torch.float32)  # schedule stays host-visible: no argmin sync later
+        sigmas = sigmas.to(device)
+        sigmas._lanpaint_host = sigmas_host
+        comfy.samplers.cast_to_load_options(self.model_options, device=device, dtype=self.model_patcher.model_dtype())
+        try:
+            self.model_patcher.pre_run()
+            output = self.inner_sample(noise, latent_image, device, sampler, sigmas, denoise_mask, callback,
+                                       disable_pbar, seed, **kwargs)
+        finally:
+            self.model_patcher.cleanup()
+        comfy.sampler_helpers.cleanup_models(self.conds, self.loaded_models)
+        del self.inner_model
+        del self.loaded_models
+        return output
+
+    def predict_noise(self, x, timestep, model_options={}, seed=None):
+        return sampling_function_LanPaint(self.inner_model, x, timestep, self.conds.get("negative", None),
+                                          self.conds.get("positive", None), self.cfg, self.cfg_BIG,
+                                          model_options=model_options, seed=seed)
+
+
+class KSamplerX0Inpaint:
+    """Per-sigma wrapper the k-diffusion sampler calls once per model evaluation
+    (nodes.py:221-315): returns the denoised latent, rewrites x in place."""
+
+    def __init__(self, model, sigmas):
+        self.inner_model = model
+        self.sigmas = sigmas
+        host = getattr(sigmas, "_lanpaint_host", None)
+        self.sigmas_host = [float(v) for v in (host if host is not None else sigmas.detach().cpu())]
+        self.audio_indicator = None
+        self.audio_shifts = None
+        self._mask_key = None
+        self._packed = None
+
+    def _latent_mask(self, denoise_mask, like):
+        """1 - (denoise_mask > 0.5), packed once per distinct mask tensor (nodes.py:281-283)."""
+        key = (denoise_mask.data_ptr(), denoise_mask._version, tuple(denoise_mask.shape))
+        if key != self._mask_key:
+            known = denoise_mask <= 0.5
+            # prepare_mask repeats one spatial mask over the channels; if so keep a single copy
+            # (1/C byte per latent element).  One sync per distinct mask tensor, not per outer step.
+            if known.ndim == like.ndim and known.shape[1] > 1 and bool((known == known[:, :1]).all()):
+                known = known[:, :1]
+            self._packed = pack_mask(known, like)
+            self._mask_key = key
+        return self._packed
+
+    def __call__(self, x, sigma, denoise_mask, model_options={}, seed=None, **kwargs):
+        mtype = self.inner_model.inner_model.model_type
+        is_flux = mtype == ModelType.FLUX
+        is_flow = mtype in FLOW_MODEL_TYPES
+        if denoise_mask is None:
+            out, _ = self.PaintMethod.unpack_model_output(
+                self.inner_model(x, sigma, model_options=model_options, seed=seed))
+        else:
+            if "denoise_mask_function" in model_options:
+                denoise_mask = model_options["denoise_mask_function"](
+                    sigma, denoise_mask, extra_options={"model": self.inner_model, "sigmas": self.sigmas})
+            sigma_host = sigma.detach().to("cpu", torch.float32)  # the one read-back of this outer step
+            times = times_from_sigma(sigma_host, is_flux or is_flow)  # reference op order, fp32 (nodes.py:242-252)
+            n_eff = effective_inner_steps(self.PaintMethod.n_steps, self.sigmas_host, float(sigma_host.mean()),
+                                          float((1.0 - times[1]).mean()), self.LanPaint_early_stop,
+                                          getattr(self, "LanPaint_min_step_frac", 1.0))
+            out = self.PaintMethod(x, self.latent_image, self.noise, sigma_host,
+                                   self._latent_mask(denoise_mask, x), times, model_options, seed, n_steps=n_eff)
+        step = model_options.get("i", kwargs.get("i", 0))
+        if step % 2 == 0:  # preview every other step (nodes.py:304-313)
+            callback = model_options.get("callback", None)
+            if callback is not None:
+                callback({"i": step, "denoised": out, "x": x})
+        return out
+
+
+class KSAMPLER(comfy.samplers.KSAMPLER):
+    """KSAMPLER.sample replacement (nodes.py:318-379): builds the per-sigma wrapper and the engine."""
+
+    def sample(self, model_wrap, sigmas, extra_args, callback, noise, latent_image=None, denoise_mask=None,
+               disable_pbar=False):
+        extra_args["denoise_mask"] = denoise_mask
+        model_k = KSamplerX0Inpaint(model_wrap, sigmas)
+        model_k.latent_image = latent_image
+        if self.inpaint_options.get("random", False):
+            generator = torch.manual_seed(extra_args.get("seed", 41) + 1)
+            model_k.noise = torch.randn(noise.shape, generator=generator, device="cpu").to(noise.dtype).to(noise.device)
+        else:
+            model_k.noise = noise
+        base = model_wrap.inner_model
+        is_flux = base.model_type == ModelType.FLUX
+        is_flow = base.model_type in FLOW_MODEL_TYPES
+        patcher = model_wrap.model_patcher
+        model_wrap.cfg_BIG = 1.0 if is_flux else patcher.LanPaint_cfg_BIG
+        noise = base.model_sampling.noise_scaling(sigmas[0], noise, latent_image, self.max_denoise(model_wrap, sigmas))
+        model_options = extra_args.get("model_options", {}) or {}
+        model_k.PaintMethod = LanPaint(
+            model_k.inner_model, patcher.LanPaint_NumSteps, patcher.LanPaint_Friction, patcher.LanPaint_Lambda,
+            patcher.LanPaint_Beta, patcher.LanPaint_StepSize, IS_FLUX=is_flux, IS_FLOW=is_flow,
+            EarlyStopThreshold=getattr(patcher, "LanPaint_InnerThreshold", 0.0),
+            EarlyStopPatience=getattr(patcher, "LanPaint_InnerPatience", 1),
+            EarlyStopHook=model_options.get("lanpaint_semantic_hook", None),
+            MinStepFrac=getattr(patcher, "LanPaint_MinStepFrac", 1.0))
+        model_k.LanPaint_early_stop = patcher.LanPaint_EarlyStop
+        model_k.LanPaint_min_step_frac = getattr(patcher, "LanPaint_MinStepFrac", 1.0)
+        total_steps = len(sigmas) - 1
+        k_callback = None
+        if callback is not None:
+            k_callback = lambda d: callback(d["i"], d["denoised"], d["x"], total_steps)  # noqa: E731
+        samples = self.sampler_function(model_k, noise, sigmas, extra_args=extra_args, callback=k_callback,
+                                        disable=disable_pbar, **self.extra_options)
+        self.last_engine = model_k.PaintMethod
+        return base.model_sampling.inverse_noise_scaling(sigmas[-1], samples)
+
+
+_override_active = False
+LAST_ENGINE = {"engine": None}  # the engine of the most recent sample call (bench/test introspection)
+
+
+@contextmanager
+def override_sample_function():
+    """Swap CFGGuider.outer_sample / .predict_noise, KSAMPLER.sample and sampler_helpers.prepare_mask for
+    the duration of one sample call; always restore; nested entry is a no-op (nodes.py:384-421)."""
+    global _override_active
+    if _override_active:
+        yield
+        return
+    _override_active = True
+    guider_cls, ksampler_cls, helpers = comfy.samplers.CFGGuider, comfy.samplers.KSAMPLER, comfy.sampler_helpers
+    saved = (guider_cls.outer_sample, guider_cls.predict_noise, ksampler_cls.sample, helpers.prepare_mask)
+
+    def sample_and_remember(self, *a, **k):
+        out = KSAMPLER.sample(self, *a, **k)
+        LAST_ENGINE["engine"] = getattr(self, "last_engine", None)
+        return out
+
+    try:
+        guider_cls.outer_sample = CFGGuider_LanPaint.outer_sample
+        guider_cls.predict_noise = CFGGuider_LanPaint.predict_noise
+        ksampler_cls.sample = sample_and_remember
+        helpers.prepare_mask = lambda noise_mask, shape, device: prepare_mask(
+            noise_mask, shape, device, video_inpainting=(len(shape) == 5))
+        yield
+    finally:
+        guider_cls.outer_sample, guider_cls.predict_noise, ksampler_cls.sample, helpers.prepare_mask = saved
+        _override_active = False
+
+
+def _ensure_model_options(model, video_inpainting):
+    if not hasattr(model, "model_options") or model.model_options is None:
+        model.model_options = {}
+    model.model_options["video_inpainting"] = video_inpainting
+
+
+# =============================================================================================
+# nodes (nodes.py:452-589, 659-808)
+# =============================================================================================
+class LanPaint_KSampler:
+    @classmethod
+    def INPUT_TYPES(s):
+        return {
+            "required": {
+                "model": ("MODEL", {"tooltip": "The model used for denoising the input latent."}),
+                "seed": ("INT", {"default": 0, "min": 0, "max": 0xffffffffffffffff, "tooltip": "The random seed used for creating the noise."}),
+                "steps": ("INT", {"default": 30, "min": 1, "max": 10000, "tooltip": "The number of steps used in the denoising process."}),
+                "cfg": ("FLOAT", {"default": 5.0, "min": 0.0, "max": 100.0, "step": 0.1, "round": 0.01, "tooltip": "The Classifier-Free Guidance scale balances creativity and adherence to the prompt. Higher values result in images more closely matching the prompt however too high values will negatively impact quality."}),
+                "sampler_name": (KSAMPLER_NAMES, {"tooltip": "Recommended: euler."}),
+                "scheduler": (comfy.samplers.KSampler.SCHEDULERS, {"default": "karras", "tooltip": "The scheduler controls how noise is gradually removed to form the image."}),
+                "positive": ("CONDITIONING", {"tooltip": "The conditioning describing the attributes you want to include in the image."}),
+                "negative": ("CONDITIONING", {"tooltip": "The conditioning describing the attributes you want to exclude from the image."}),
+                "latent_image": ("LATENT", {"tooltip": "The latent image to denoise."}),
+                "denoise": ("FLOAT", {"default": 1.0, "min": 0.0, "max": 1.0, "step": 0.01, "tooltip": "The amount of denoising applied, lower values will maintain the structure of the initial image allowing for image to image sampling."}),
+                "LanPaint_NumSteps": _w_num_steps(_TIP_STEPS_K),
+                "LanPaint_PromptMode": _w_prompt_mode(_TIP_MODE_K),
+                "LanPaint_Info": _w_info("LanPaint KSampler."),
+                "Inpainting_mode": _w_mode(),
+            },
+            "hidden": _hidden(("LanPaint_MinStepFrac",)),
+        }
+
+    RETURN_TYPES = ("LATENT",)
+    OUTPUT_TOOLTIPS = ("The denoised latent.",)
+    FUNCTION = "sample"
+    CATEGORY = "sampling"
+    DESCRIPTION = "Uses the provided model, positive and negative conditioning to denoise the latent image."
+
+    def sample(self, model, seed, steps, cfg, sampler_name, scheduler, positive, negative, latent_image, denoise=1.0,
+               LanPaint_NumSteps=5, LanPaint_PromptMode="Image First", LanPaint_Info="", Inpainting_mode=IMAGE_MODE,
+               **kwargs):
+        n = _sanitize_param(LanPaint_NumSteps, 5)
+        mode = _sanitize_param(LanPaint_PromptMode, "Image First", allowed=PROMPT_MODES)
+        imode = _sanitize_param(Inpainting_mode, IMAGE_MODE, allowed=(IMAGE_MODE, VIDEO_MODE))
+        _set_hyper(model, num_steps=n, cfg=cfg, prompt_mode=mode)
+        _ensure_model_options(model, imode == VIDEO_MODE)
+        with override_sample_function():
+            return comfy_nodes_module.common_ksampler(model, seed, steps, cfg, sampler_name, scheduler, positive,
+                                                      negative, latent_image, denoise=denoise)
+
+
+class LanPaint_KSamplerAdvanced:
+    @classmethod
+    def INPUT_TYPES(s):
+        return {
+            "required": {
+                "model": ("MODEL",),
+                "add_noise": (["enable", "disable"],),
+                "noise_seed": ("INT", {"default": 0, "min": 0, "max": 0xffffffffffffffff}),
+                "steps": ("INT", {"default": 30, "min": 1, "max": 10000}),
+                "cfg": ("FLOAT", {"default": 5.0, "min": 0.0, "max": 100.0, "step": 0.1, "round": 0.01}),
+                "sampler_name": (KSAMPLER_NAMES,),
+                "scheduler": (comfy.samplers.KSampler.SCHEDULERS,),
+                "positive": ("CONDITIONING",),
+                "negative": ("CONDITIONING",),
+                "latent_image": ("LATENT",),
+                "start_at_step": ("INT", {"default": 0, "min": 0, "max": 10000}),
+                "end_at_step": ("INT", {"default": 10000, "min": 0, "max": 10000}),
+                "return_with_leftover_noise": (["disable", "enable"],),
+                "LanPaint_NumSteps": _w_num_steps(_TIP_STEPS_K),
+                "LanPaint_Lambda": ("FLOAT", {"default": 5.0, "min": 0.1, "max": 50.0, "step": 0.1, "round": 0.1, "tooltip": "The bidirectional guidance scale. Higher values align with known regions more closely, but may result in instability."}),
+                "LanPaint_StepSize": ("FLOAT", {"default": 0.2, "min": 0.0001, "max": 1., "step": 0.01, "round": 0.001, "tooltip": "The step size for the Langevin dynamics. Higher values result in faster convergence but may be unstable."}),
+                "LanPaint_PromptMode": _w_prompt_mode(_TIP_MODE_K),
+                "LanPaint_Info": _w_info("LanPaint KSampler Adv."),
+                "Inpainting_mode": _w_mode(),
+            },
+            "hidden": _hidden(_RETIRED_ALL),
+        }
+
+    RETURN_TYPES = ("LATENT",)
+    FUNCTION = "sample"
+    CATEGORY = "sampling"
+
+    def sample(self, model, add_noise, noise_seed, steps, cfg, sampler_name, scheduler, positive, negative,
+               latent_image, start_at_step, end_at_step, return_with_leftover_noise, LanPaint_NumSteps=5,
+               LanPaint_Lambda=5.0, LanPaint_StepSize=0.2, LanPaint_PromptMode="Image First", LanPaint_Info="",
+               Inpainting_mode=IMAGE_MODE, **kwargs):
+        n = _sanitize_param(LanPaint_NumSteps, 5)
+        lam = _sanitize_param(LanPaint_Lambda, 5.0)
+        step = _sanitize_param(LanPaint_StepSize, 0.2)
+        mode = _sanitize_param(LanPaint_PromptMode, "Image First", allowed=PROMPT_MODES)
+        imode = _sanitize_param(Inpainting_mode, IMAGE_MODE, allowed=(IMAGE_MODE, VIDEO_MODE))
+        _set_hyper(model, num_steps=n, cfg=cfg, prompt_mode=mode, lam=lam, step_size=step)
+        _ensure_model_options(model, imode == VIDEO_MODE)
+        with override_sample_function():
+            return comfy_nodes_module.common_ksampler(
+                model, noise_seed, steps, cfg, sampler_name, scheduler, positive, negative, latent_image, denoise=1.0,
+                disable_noise=(add_noise == "disable"), start_step=start_at_step, last_step=end_at_step,
+                force_full_denoise=(return_with_leftover_noise != "enable"))
+
+
+class Noise_EmptyNoise:
+    def generate_noise(self, latent):
+        return torch.zeros_like(latent["samples"])
+
+
+class Noise_RandomNoise:
+    def __init__(self, seed):
+        self.seed = seed
+
+    def generate_noise(self, latent):
+        torch.manual_seed(self.seed)
+        return torch.randn_like(latent["samples"])
+
+
+def _finish_custom(model_for_preview, latent, samples, x0_output):
+    out = latent.copy()
+    out["samples"] = samples
+    if "x0" in x0_output:
+        den = latent.copy()
+        den["samples"] = model_for_preview.model.process_latent_out(x0_output["x0"].cpu())
+        return out, den
+    return out, out
+
+
+class LanPaint_SamplerCustom:
+    @classmethod
+    def INPUT_TYPES(s):
+        return {"required": {
+            "model": ("MODEL",),
+            "add_noise": ("BOOLEAN", {"default": True}),
+            "noise_seed": ("INT", {"default": 0, "min": 0, "max": 0xffffffffffffffff, "control_after_generate": True}),
+            "cfg": ("FLOAT", {"default": 8.0, "min": 0.0, "max": 100.0, "step": 0.1, "round": 0.01}),
+            "positive": ("CONDITIONING",),
+            "negative": ("CONDITIONING",),
+            "sampler": ("SAMPLER",),
+            "sigmas": ("SIGMAS",),
+            "latent_image": ("LATENT",),
+            "LanPaint_NumSteps": _w_num_steps(_TIP_STEPS_C),
+            "LanPaint_PromptMode": _w_prompt_mode(_TIP_MODE_C),
+            "LanPaint_Info": _w_info("LanPaint Custom Sampler."),
+        }}
+
+    RETURN_TYPES = ("LATENT", "LATENT")
+    RETURN_NAMES = ("output", "denoised_output")
+    FUNCTION = "sample"
+    CATEGORY = "sampling/custom_sampling"
+
+    def sample(self, model, sampler, sigmas, add_noise, noise_seed, cfg, positive, negative, latent_image,
+               LanPaint_NumSteps, LanPaint_PromptMode, LanPaint_Info=""):
+        n = _sanitize_param(LanPaint_NumSteps, 5)
+        mode = _sanitize_param(LanPaint_PromptMode, "Image First", allowed=PROMPT_MODES)
+        _set_hyper(model, num_steps=n, cfg=cfg, prompt_mode=mode)
+        with override_sample_function():
+            latent = latent_image.copy()
+            latent["samples"] = comfy.sample.fix_empty_latent_channels(model, latent["samples"])
+            noise = (Noise_RandomNoise(noise_seed) if add_noise else Noise_EmptyNoise()).generate_noise(latent)
+            x0_output = {}
+            callback = latent_preview.prepare_callback(model, sigmas.shape[-1] - 1, x0_output)
+            samples = comfy.sample.sample_custom(model, noise, cfg, sampler, sigmas, positive, negative,
+                                                 latent["samples"], noise_mask=latent.get("noise_mask"),
+                                                 callback=callback, disable_pbar=not comfy.utils.PROGRESS_BAR_ENABLED,
+                                                 seed=noise_seed)
+            return _finish_custom(model, latent, samples, x0_output)
+
+
+class LanPaint_SamplerCustomAdvanced:
+    @classmethod
+    def INPUT_TYPES(s):
+        return {
+            "required": {
+                "noise": ("NOISE",),
+                "guider": ("GUIDER",),
+                "sampler": ("SAMPLER",),
+                "sigmas": ("SIGMAS",),
+                "latent_image": ("LATENT",),
+                "LanPaint_NumSteps": _w_num_steps(_TIP_STEPS_C),
+                "LanPaint_Lambda": ("FLOAT", {"default": 5.0, "min": 0.1, "max": 50.0, "step": 0.1, "tooltip": "Bidirectional guidance scale. Higher values align with known regions but may cause instability."}),
+                "LanPaint_StepSize": ("FLOAT", {"default": 0.2, "min": 0.0001, "max": 1.0, "step": 0.01, "tooltip": "Step size for Langevin dynamics. Higher values speed convergence but may be unstable."}),
+                "LanPaint_PromptMode": _w_prompt_mode(_TIP_MODE_C),
+                "LanPaint_Info": _w_info("LanPaint Custom Sampler Adv."),
+            },
+            "hidden": _hidden(_RETIRED_ALL),
+        }
+
+    RETURN_TYPES = ("LATENT", "LATENT")
+    RETURN_NAMES = ("output", "denoised_output")
+    FUNCTION = "sample"
+    CATEGORY = "sampling/custom_sampling"
+
+    def sample(self, noise, guider, sampler, sigmas, latent_image, LanPaint_NumSteps, LanPaint_Lambda,
+               LanPaint_StepSize, LanPaint_PromptMode, LanPaint_Info="", **kwargs):
+        n = _sanitize_param(LanPaint_NumSteps, 5)
+        lam = _sanitize_param(LanPaint_Lambda, 5.0)
+        step = _sanitize_param(LanPaint_StepSize, 0.2)
+        mode = _sanitize_param(LanPaint_PromptMode, "Image First", allowed=PROMPT_MODES)
+        patcher = guider.model_patcher
+        _set_hyper(patcher, num_steps=n, cfg=guider.cfg, prompt_mode=mode, lam=lam, step_size=step)
+        with override_sample_function():
+            latent = latent_image.copy()
+            latent["samples"] = comfy.sample.fix_empty_latent_channels(patcher, latent_image["samples"])
+            x0_output = {}
+            callback = latent_preview.prepare_callback(patcher, sigmas.shape[-1] - 1, x0_output)
+            samples = guider.sample(noise.generate_noise(latent), latent["samples"], sampler, sigmas,
+                                    denoise_mask=latent.get("noise_mask"), callback=callback,
+                                    disable_pbar=not comfy.utils.PROGRESS_BAR_ENABLED, seed=noise.seed)
+            samples = samples.to(comfy.model_management.intermediate_device())
+            return _finish_custom(patcher, latent, samples, x0_output)
+
+
+NODE_CLASS_MAPPINGS = {
+    "LanPaint_KSampler": LanPaint_KSampler,
+    "LanPaint_KSamplerAdvanced": LanPaint_KSamplerAdvanced,
+    "LanPaint_SamplerCustom": LanPaint_SamplerCustom,
+    "LanPaint_SamplerCustomAdvanced": LanPaint_SamplerCustomAdvanced,
+}
+
+NODE_DISPLAY_NAME_MAPPINGS = {
+    "LanPaint_KSampler": "LanPaint KSampler",
+    "LanPaint_KSamplerAdvanced": "LanPaint KSampler (Advanced)",
+    "LanPaint_SamplerCustom": "LanPaint Sampler Custom",
+    "LanPaint_SamplerCustomAdvanced": "LanPaint Sampler Custom (Advanced)",
+}

@@ -145,11 +145,14 @@ class LanPaint:
                       independent B=1 request; uses model_sampling.noise_scaling's form)
       replace_mode    "probe" (derive the linear form of noise_scaling from a 4-point host
                       probe; falls back to "call" if it is not linear) | "call"
+      cuda_graph      False | True: capture the whole outer step (model calls included) into one
+                      CUDA graph per (shape, sub-step count) and replay it; falls back to eager
+                      launches if the model is not capture-safe
     """
 
     def __init__(self, Model, NSteps, Friction, Lambda, Beta, StepSize, IS_FLUX=False, IS_FLOW=False,
                  EarlyStopThreshold=0.0, EarlyStopPatience=1, EarlyStopHook=None, MinStepFrac=0.0, *,
-                 rng="torch", batched_replace="reference", replace_mode="probe"):
+                 rng="torch", batched_replace="reference", replace_mode="probe", cuda_graph=False):
         self.n_steps = NSteps
         self.chara_lamb = Lambda
         self.IS_FLUX = IS_FLUX
@@ -166,6 +169,9 @@ class LanPaint:
         self.rng = rng
         self.batched_replace = batched_replace
         self.replace_mode = replace_mode
+        self.cuda_graph = cuda_graph
+        self._graphs = {}
+        self._graph_statics = {}
         # statistics a caller (bench, tests) can read back
         self.launches = 0
         self.model_calls = 0
@@ -173,6 +179,7 @@ class LanPaint:
         self._mask_cache = _IdentityCache()
         self._noise_zero_cache = _IdentityCache()
         self._ws = {}
+        self.kernel_timer = None  # set to a list to collect (flags, start_event, stop_event) per substep launch
         _native.load()  # fail at construction, loudly, if the CUDA library is absent
 
     # ---- small helpers kept for API compatibility (lanpaint.py:23-43) ----------
@@ -224,9 +231,13 @@ class LanPaint:
         if mode != "probe":
             return None
         rn, ry = [], []
+        seen = {}
         for s in (sigma_host if not scalar_sigma else sigma_host[:1]):
-            form = _probe_noise_scaling(sampling, float(s))
-            if form is None:
+            s = float(s)
+            form = seen.get(s)
+            if form is None:  # one probe per distinct sigma, not per sample
+                form = seen[s] = _probe_noise_scaling(sampling, s) or False
+            if form is False:
                 return None
             rn.append(form[0])
             ry.append(form[1])
@@ -277,7 +288,7 @@ class LanPaint:
         rng = opts.get("rng", self.rng)
         batched = opts.get("batched_replace", self.batched_replace)
         rmode = opts.get("replace_mode", self.replace_mode)
-        lib = _native.load()
+        use_graph = opts.get("cuda_graph", self.cuda_graph)
         dev = x.device
         flow = bool(IS_FLUX or IS_FLOW)
         if self.audio_indicator is not None and self.current_times_audio is not None:
@@ -290,16 +301,19 @@ class LanPaint:
         spatial = int(np.prod(x.shape[2:])) if x.ndim > 2 else 1
         VE_Sigma, abt, Flow_t = current_times
 
-        # ---- one host read-back of the per-sample scalars ----
-        def flat(t):
-            t = t.reshape(-1).to(device=dev, dtype=torch.float32)
+        # ---- per-sample scalars on the host: one read-back, or none if the caller already holds
+        # sigma / current_times as CPU tensors (the sync-free path bench.py and the graphed runner use)
+        def flat(t, where):
+            t = t.reshape(-1).to(device=where, dtype=torch.float32)
             return t if t.numel() == B else t.expand(B)
-        host = torch.stack([flat(sigma), flat(VE_Sigma), flat(abt)]).cpu().numpy()
-        sigma_h, ve_h, abt_h = host[0], host[1], host[2]
+        t_model_src = Flow_t if flow else VE_Sigma
+        scal = (sigma, VE_Sigma, abt, t_model_src)
+        where = torch.device("cpu") if all(t.device.type == "cpu" for t in scal) else dev
+        host = torch.stack([flat(t, where) for t in scal]).cpu().numpy()
+        sigma_h, ve_h, abt_h, tm_h = host[0], host[1], host[2], host[3]
         hyper = Hyper(self.step_size, self.chara_lamb, self.chara_beta, self.min_step_frac, flow)
 
         # ---- operands ----
-        xm = x if (x.dtype == torch.float32 and x.is_contiguous()) else _f32c(x).clone()
         y = _f32c(self.latent_image if self.latent_image.device == dev else self.latent_image.to(dev))
         nz = _f32c(self.noise if self.noise.device == dev else self.noise.to(dev))
         pm = self._mask_cache.get(latent_mask) if isinstance(latent_mask, torch.Tensor) else None
@@ -310,35 +324,59 @@ class LanPaint:
             self._mask_cache.put(latent_mask, pm)
             self.launches += 1
         dims = _native.Dims(B, per_row, spatial, pm.row_stride, pm.channel_stride)
-        ws = self._workspace(xm, B)
-        stream = _P(_stream_ptr(dev))
 
         scalar_sigma = sigma.numel() == 1
         form = self._replace_form(sigma_h, scalar_sigma, B, rmode, batched)
-        if form is None:  # opaque noise_scaling: call it like the reference does (lanpaint.py:88)
-            sampling = self.inner_model.inner_model.model_sampling
-            known = _f32c(sampling.noise_scaling(self.add_none_dims(sigma), nz, y))
-            rep_n, rep_y, noise_arg = np.ones(B), np.zeros(B), known
+        if form is None:
+            rep_n, rep_y = np.ones(B), np.zeros(B)  # `known` is computed by noise_scaling itself (lanpaint.py:88)
         else:
             rep_n, rep_y = form
-            noise_arg = nz
         table_np = build_table(abt_h, ve_h, hyper, rep_n, rep_y)
+
+        # lanpaint.py:205: a non-positive mean step skips the dynamics (and its model calls)
+        active = n_steps if mean_half_dt(abt_h, hyper) > 0.0 else 0
+        plan = _DrawPlan(rng, x, active)
+
+        if use_graph and stopper is None and plan.mode != _native.RNG_TAPE:
+            out = self._graphed_step(x, y, nz, pm, dims, table_np, tm_h, sigma_h, sigma.shape, active, plan,
+                                     form is None, model_options, seed)
+            if out is not None:
+                plan.finish()
+                self.substeps_done += active
+                return out if out.dtype == input_x.dtype else out.to(input_x.dtype)
+
+        xm = x if (x.dtype == torch.float32 and x.is_contiguous()) else _f32c(x)
+        ws = self._workspace(xm, B)
         tab = ws["table_dev"]
         tab.copy_(torch.from_numpy(table_np))  # pageable H2D: staged before this returns, no aliasing hazard
+        t_model = torch.from_numpy(tm_h).to(dev) if t_model_src.device.type == "cpu" else t_model_src.reshape(-1)
+        sigma_dev = sigma.to(dev)
+        out = torch.empty_like(xm)
+        done = self._launch_sequence(xm, y, nz, pm, dims, tab, t_model, sigma_dev, ws["c"], out, active, plan,
+                                     form is None, model_options, seed, stopper, None)
+        plan.finish()
+        self.substeps_done += done
+        if xm is not input_x:
+            input_x.copy_(xm)
+        return out if out.dtype == input_x.dtype else out.to(input_x.dtype)
 
-        # ---- prologue: replace step + change of variables (lanpaint.py:85-99) ----
+    # ---- the launch sequence of one outer step (shared by the eager path and graph capture) ----
+    def _launch_sequence(self, xm, y, nz, pm, dims, tab, t_model, sigma_dev, cbuf, out, active, plan, call_scaling,
+                         model_options, seed, stopper, rng_state):
+        lib = _native.load()
+        dev = xm.device
+        stream = _P(_stream_ptr(dev))
+        F = _native
+        noise_arg = nz
+        if call_scaling:  # opaque noise_scaling: call it like the reference does (lanpaint.py:88)
+            sampling = self.inner_model.inner_model.model_sampling
+            noise_arg = _f32c(sampling.noise_scaling(self.add_none_dims(sigma_dev), nz, y))
+        # prologue: replace step + change of variables (lanpaint.py:85-99)
         rc = lib.lp_prologue_f32(_P(xm.data_ptr()), _P(y.data_ptr()), _P(noise_arg.data_ptr()),
                                  _P(pm.data.data_ptr()), _P(xm.data_ptr()), None, _P(tab.data_ptr()),
                                  C.byref(dims), stream)
         _native.check(rc, "lp_prologue_f32")
         self.launches += 1
-
-        # lanpaint.py:205: a non-positive mean step skips the dynamics (and its model calls)
-        active = n_steps if mean_half_dt(abt_h, hyper) > 0.0 else 0
-        t_model = (Flow_t if flow else VE_Sigma).reshape(-1)
-        draws = _DrawPlan(rng, xm, active)
-        cbuf = ws["c"]
-        F = _native
         done = 0
         for i in range(active):
             heads = self.inner_model(xm, t_model, model_options=model_options, seed=seed)
@@ -351,10 +389,13 @@ class LanPaint:
             if stopper is None:
                 # fused: post-model half of sub-step i + pre-model half of sub-step i+1
                 flags = (F.SUBSTEP_FIRST if first else 0) | (F.SUBSTEP_FUSE_NEXT if has_next else 0)
-                r = draws.rng_struct(2 if has_next else 1)
+                r = plan.rng_struct(2 if has_next else 1, rng_state)
+                ev = self._event_pair(flags) if self.kernel_timer is not None else None
                 rc = lib.lp_substep_f32(_P(xm.data_ptr()), _P(x0.data_ptr()), _P(x0b.data_ptr()),
                                         _P(y.data_ptr()), _P(pm.data.data_ptr()), _P(cbuf.data_ptr()), None, None,
                                         _P(tab.data_ptr()), C.byref(dims), C.byref(r), flags, stream)
+                if ev is not None:
+                    ev[1].record()
                 _native.check(rc, "lp_substep_f32")
                 self.launches += 1
                 done += 1
@@ -363,7 +404,7 @@ class LanPaint:
             # first half-advance of sub-step i+1 is applied, so that half runs as its own launch
             flags = (F.SUBSTEP_FIRST if first else 0) | F.SUBSTEP_STORE_C
             x0e = stopper.next_x0e_buffer(xm)
-            r = draws.rng_struct(1)
+            r = plan.rng_struct(1, rng_state)
             rc = lib.lp_substep_f32(_P(xm.data_ptr()), _P(x0.data_ptr()), _P(x0b.data_ptr()), _P(y.data_ptr()),
                                     _P(pm.data.data_ptr()), _P(cbuf.data_ptr()), None, _P(x0e.data_ptr()),
                                     _P(tab.data_ptr()), C.byref(dims), C.byref(r), flags, stream)
@@ -373,27 +414,130 @@ class LanPaint:
             if stopper.step(i, active, xm, cbuf, x0e, seed):
                 break
             if has_next:
-                r = draws.rng_struct(1)
+                r = plan.rng_struct(1, rng_state)
                 rc = lib.lp_advance_f32(_P(xm.data_ptr()), _P(cbuf.data_ptr()), _P(pm.data.data_ptr()),
                                         _P(tab.data_ptr()), C.byref(dims), C.byref(r), 1, stream)
                 _native.check(rc, "lp_advance_f32")
                 self.launches += 1
-        draws.finish()
-        self.substeps_done += done
 
-        # ---- final denoise + known-region paste (lanpaint.py:151-157) ----
-        out_heads = self.inner_model(xm, sigma, model_options=model_options, seed=seed)
+        # final denoise + known-region paste (lanpaint.py:151-157)
+        out_heads = self.inner_model(xm, sigma_dev, model_options=model_options, seed=seed)
         self.model_calls += 1
         mo, _ = self.unpack_model_output(out_heads)
         mo = _as_operand(mo, xm)
-        out = torch.empty_like(xm)
         rc = lib.lp_epilogue_f32(_P(mo.data_ptr()), _P(y.data_ptr()), _P(pm.data.data_ptr()), _P(out.data_ptr()),
                                  C.byref(dims), stream)
         _native.check(rc, "lp_epilogue_f32")
         self.launches += 1
-        if xm is not input_x:
-            input_x.copy_(xm)
-        return out if out.dtype == input_x.dtype else out.to(input_x.dtype)
+        return done
+
+    # ---- CUDA-graph replay of a whole outer step -------------------------------------------------
+    def _graphed_step(self, x, y, nz, pm, dims, table_np, tm_h, sigma_h, sigma_shape, active, plan, call_scaling,
+                      model_options, seed):
+        """Replay (capturing on first use) one CUDA graph holding the whole outer step: prologue,
+        `active` x (model call + fused sub-step), final model call, epilogue.  Everything that changes
+        between outer steps -- coefficient table, model timestep, sigma, RNG position -- lives in one
+        small device block refreshed by a single H2D copy, so one graph serves every sigma of the
+        schedule with the same sub-step count.  Returns None if capture is not possible (the caller
+        then runs eagerly)."""
+        dev = x.device
+        B = x.shape[0]
+        key = (dev, tuple(x.shape), active, plan.mode, bool(call_scaling), tuple(sigma_shape),
+               pm.row_stride, pm.channel_stride)
+        g = self._graphs.get(key)
+        if g is False:
+            return None
+        st = self._graph_static(x, y, nz, pm, B)
+        n_par = B * _native.TABLE_STRIDE + 2 * B + 4
+        # ---- the dynamic block: [table | t_model | sigma | seed, base (2 x u64 in 4 float slots)] ----
+        host = np.empty(n_par, dtype=np.float32)
+        host[:B * _native.TABLE_STRIDE] = table_np.reshape(-1)
+        o = B * _native.TABLE_STRIDE
+        host[o:o + B] = tm_h
+        host[o + B:o + 2 * B] = sigma_h
+        host[o + 2 * B:].view(np.uint64)[:] = plan.state_words()
+        if g is None:
+            g = self._capture(key, st, dims, B, host, sigma_shape, active, plan, call_scaling, model_options, seed)
+            if g is None:
+                self._graphs[key] = False
+                return None
+        g["params"].copy_(torch.from_numpy(host))
+        st["x"].copy_(x)
+        g["graph"].replay()
+        self.launches += g["launches"]
+        self.model_calls += g["model_calls"]
+        plan.consume(2 * active - 1 if active > 0 else 0)
+        x.copy_(st["x"])            # the in-place contract of lanpaint.py:156
+        return g["out"].clone()     # a fresh tensor, like the reference returns
+
+    def _graph_static(self, x, y, nz, pm, B):
+        """Static operand buffers the graphs are captured against; refreshed when the source changes."""
+        key = (x.device, tuple(x.shape))
+        st = self._graph_statics.get(key)
+        if st is None:
+            st = {"x": torch.empty_like(x, dtype=torch.float32, memory_format=torch.contiguous_format),
+                  "y": torch.empty_like(y), "nz": torch.empty_like(nz), "mask": torch.empty_like(pm.data),
+                  "c": torch.empty_like(y), "src": [None, None, None]}
+            self._graph_statics = {key: st}
+            self._graphs = {}
+        for slot, (name, src) in enumerate((("y", y), ("nz", nz), ("mask", pm.data))):
+            ident = (src.data_ptr(), src._version, tuple(src.shape))
+            if st["src"][slot] != ident:
+                if st[name].shape != src.shape:
+                    st[name] = torch.empty_like(src)
+                    self._graphs = {}
+                st[name].copy_(src)
+                st["src"][slot] = ident
+        return st
+
+    def _capture(self, key, st, dims, B, host, sigma_shape, active, plan, call_scaling, model_options, seed):
+        dev = st["x"].device
+        params = torch.from_numpy(host).to(dev)
+        o = B * _native.TABLE_STRIDE
+        tab = params[:o].view(B, _native.TABLE_STRIDE)
+        t_model = params[o:o + B]
+        sigma_dev = params[o + B:o + 2 * B].view(sigma_shape) if int(np.prod(sigma_shape)) == B else params[o + B:o + B + 1].view(sigma_shape)
+        rng_state = params[o + 2 * B:].data_ptr()
+        if rng_state % 8 != 0:
+            return None
+        out = torch.empty_like(st["x"])
+        pm = PackedMask(st["mask"], key[6], key[7])
+        rel = plan.relative()
+        counts = (self.launches, self.model_calls)
+
+        def body():
+            rel.reset()
+            self._launch_sequence(st["x"], st["y"], st["nz"], pm, dims, tab, t_model, sigma_dev, st["c"], out, active,
+                                  rel, call_scaling, model_options, seed, None, rng_state)
+        try:
+            timer, self.kernel_timer = self.kernel_timer, None
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                body()  # warm-up outside capture: lazy inits, allocator
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.launches, self.model_calls = counts
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+        except Exception as e:  # capture-unsafe model: run eagerly instead, say so once
+            import warnings
+            warnings.warn(f"lanpaint_b200: CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly")
+            self.launches, self.model_calls = counts
+            self.kernel_timer = timer
+            return None
+        self.kernel_timer = timer
+        g = {"graph": graph, "params": params, "out": out,
+             "launches": self.launches - counts[0], "model_calls": self.model_calls - counts[1]}
+        self.launches, self.model_calls = counts
+        self._graphs[key] = g
+        return g
+
+    def _event_pair(self, flags):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        self.kernel_timer.append((flags, a, b))
+        return a, b
 
     def _make_stopper(self, model_options, latent_mask, abt):
         semantic = model_options.get("lanpaint_semantic_stop") if isinstance(model_options, dict) else None
@@ -463,8 +607,9 @@ class _DrawPlan:
             raise ValueError(f"unknown rng {rng!r}: use 'torch', 'philox' or a NoiseTape")
         self._keep: List[torch.Tensor] = []
 
-    def rng_struct(self, k: int) -> _native.Rng:
-        """rng argument of a launch that consumes the next k (1 or 2) draws."""
+    def rng_struct(self, k: int, state_ptr=None) -> _native.Rng:
+        """rng argument of a launch that consumes the next k (1 or 2) draws.  With `state_ptr`
+        (graph capture) the positions are relative to the {seed, base} block the kernel reads."""
         r = _native.Rng()
         r.mode = self.mode
         if self.mode == _native.RNG_TAPE:
@@ -474,15 +619,34 @@ class _DrawPlan:
             r.tape0 = t0.data_ptr()
             r.tape1 = None if t1 is None else t1.data_ptr()
         else:
-            r.seed = self.seed
-            if self.mode == _native.RNG_TORCH:
-                r.draw0 = self.offset + self.used * self.inc
-                r.draw1 = self.offset + (self.used + 1) * self.inc
-            else:  # counter-based: one 128-bit block per 4 elements per draw
-                r.draw0 = self.offset // 4 + self.used
-                r.draw1 = self.offset // 4 + self.used + 1
+            rel = state_ptr is not None
+            r.seed = 0 if rel else self.seed
+            r.state = state_ptr
+            step = self.inc if self.mode == _native.RNG_TORCH else 1
+            base = 0 if rel else (self.offset if self.mode == _native.RNG_TORCH else self.offset // 4)
+            r.draw0 = base + self.used * step
+            r.draw1 = base + (self.used + 1) * step
         self.used += k
         return r
+
+    def relative(self):
+        """A plan used while capturing: counts draws from zero, touches no generator."""
+        p = object.__new__(_DrawPlan)
+        p.__dict__.update(self.__dict__)
+        p.gen = None
+        p.used = 0
+        return p
+
+    def reset(self):
+        self.used = 0
+
+    def consume(self, k: int):
+        self.used += k
+
+    def state_words(self):
+        """{seed, base} as the kernels read them through lp_rng.state."""
+        base = self.offset if self.mode == _native.RNG_TORCH else self.offset // 4
+        return np.array([self.seed, base], dtype=np.uint64)
 
     def finish(self):
         """Advance the global generator by what the reference would have consumed."""

@@ -130,3 +130,78 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# --------------------------------------------------------------------------------------------
+# node API dump: INPUT_TYPES / RETURN_TYPES / ... of the reference's four sampler nodes
+# --------------------------------------------------------------------------------------------
+RESHAPE_CASES = {
+    "img2d": ((64, 48), (2, 4, 8, 6), False),
+    "img3d": ((1, 64, 64), (1, 16, 8, 8), False),
+    "img4d": ((1, 1, 40, 40), (1, 4, 10, 10), False),
+    "img_to_5d": ((64, 64), (1, 16, 3, 8, 8), False),
+    "vid_frames_on_batch": ((17, 1, 32, 32), (1, 16, 5, 4, 4), True),
+    "vid_raw_fhw": ((17, 32, 32), (1, 16, 5, 4, 4), True),
+    "vid_still": ((32, 32), (1, 16, 5, 4, 4), True),
+}
+
+
+def dump_node_api():
+    import importlib
+    import types
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    comfy = stub("comfy")
+    comfy.__path__ = []
+    def _repeat(t, n):  # comfy.utils.repeat_to_batch_size semantics
+        if t.shape[0] >= n:
+            return t[:n]
+        reps = (n + t.shape[0] - 1) // t.shape[0]
+        return t.repeat((reps,) + (1,) * (t.ndim - 1))[:n]
+
+    comfy.utils = stub("comfy.utils", repeat_to_batch_size=_repeat)
+    comfy.samplers = stub("comfy.samplers", KSAMPLER=type("KSAMPLER", (), {}),
+                          KSampler=type("KSampler", (), {"SCHEDULERS": ["<SCHEDULERS>"]}))
+    comfy.model_base = stub("comfy.model_base", ModelType=types.SimpleNamespace(FLUX="FLUX", FLOW="FLOW"),
+                            WAN22=type("WAN22", (), {}))
+    stub("nodes")
+    stub("latent_preview")
+    stub("comfyui_version", __version__="0.6.0")
+    ref = importlib.import_module("src.LanPaint.nodes")
+    api = {}
+    for name in ("LanPaint_KSampler", "LanPaint_KSamplerAdvanced", "LanPaint_SamplerCustom",
+                 "LanPaint_SamplerCustomAdvanced"):
+        cls = ref.NODE_CLASS_MAPPINGS[name]
+        api[name] = {
+            "INPUT_TYPES": cls.INPUT_TYPES(),
+            "RETURN_TYPES": list(cls.RETURN_TYPES),
+            "RETURN_NAMES": list(getattr(cls, "RETURN_NAMES", ())),
+            "FUNCTION": cls.FUNCTION,
+            "CATEGORY": cls.CATEGORY,
+            "display_name": ref.NODE_DISPLAY_NAME_MAPPINGS[name],
+        }
+    api["KSAMPLER_NAMES"] = list(ref.KSAMPLER_NAMES)
+    # reshape_mask known answers (mask prep runs once per sample; kept for drop-in behaviour)
+    g = torch.Generator().manual_seed(7)
+    cases = {}
+    for key, (mshape, oshape, video) in RESHAPE_CASES.items():
+        m = (torch.rand(mshape, generator=g) > 0.6).float()
+        cases["in_" + key] = m.numpy()
+        cases["out_" + key] = ref.reshape_mask(m, oshape, video).contiguous().numpy()
+    np.savez_compressed(os.path.join(HERE, "reshape_mask_cases.npz"), **cases)
+    with open(os.path.join(HERE, "node_api.json"), "w") as f:
+        json.dump(api, f, indent=1, ensure_ascii=False, sort_keys=False)
+    for n in ("comfy", "comfy.utils", "comfy.samplers", "comfy.model_base", "nodes", "latent_preview",
+              "comfyui_version", "src.LanPaint.nodes"):
+        sys.modules.pop(n, None)
+    print("node_api.json written")
+
+
+if __name__ == "__main__" and "--api" in sys.argv:
+    dump_node_api()

@@ -360,3 +360,52 @@ def test_synth_denoiser_kernel_matches_torch(cuda_device):
     assert rc == 0
     w0, w1 = make_model("two_heads", False)(x, None)
     assert max_rel(h0, w0) <= 1e-6 and max_rel(h1, w1) <= 1e-6
+
+
+# ----------------------------------------------------------------------------
+# 5. CUDA-graph replay of whole outer steps
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("rng", ["philox", "torch"])
+def test_graph_replay_equals_eager_launches(rng, cuda_device):
+    from lanpaint_b200.runner import SynthDenoiser, VESampling
+    dev = cuda_device
+    shape = (4, 4, 64, 64)
+    x, y, noise, m = synth_inputs(shape, seed=21, device=dev)
+    res = {}
+    for mode in (False, True):
+        torch.manual_seed(9)
+        eng = _engine(SynthDenoiser(VESampling()), dict(n_steps=5), rng=rng, cuda_graph=mode,
+                      batched_replace="per_sample")
+        outs = []
+        xx = x.clone()
+        for sig_v, n in ((9.0, 5), (3.0, 5), (1.0, 3), (0.2, 0)):   # two sigmas share the n=5 graph
+            sig = torch.full((4,), sig_v)                              # CPU-resident: the sync-free path
+            times = O.times_from_sigma(sig, False)
+            outs.append(eng(xx, y, noise, sig, m, tuple(times), None, 0, n_steps=n).clone())
+        res[mode] = (outs, xx.clone(), eng, torch.cuda.default_generators[dev.index].get_offset())
+    for a, b in zip(res[False][0], res[True][0]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[False][1], res[True][1])
+    assert res[False][3] == res[True][3]                  # generator advanced identically
+    g = res[True][2]
+    assert len([v for v in g._graphs.values() if v]) == 3  # n = 5, 3, 0 -> three graphs, sigma is data
+    assert g.launches == res[False][2].launches and g.model_calls == res[False][2].model_calls
+
+
+def test_graph_capture_failure_falls_back_to_eager(cuda_device):
+    class Syncing(O.PointwiseDenoiser):
+        def __call__(self, x, sigma, model_options=None, seed=None):
+            float(x.sum())  # a host sync: illegal under stream capture
+            return super().__call__(x, sigma)
+    dev = cuda_device
+    shape = (1, 4, 16, 16)
+    x, y, noise, m = synth_inputs(shape, seed=2, device=dev)
+    sig = torch.tensor([2.0])
+    times = O.times_from_sigma(sig, False)
+    torch.manual_seed(3)
+    eng = _engine(Syncing(O.VESampling()), dict(n_steps=2), rng="philox", cuda_graph=True)
+    with pytest.warns(UserWarning, match="capture failed"):
+        out = eng(x.clone(), y, noise, sig, m, tuple(times), None, 0, n_steps=2)
+    torch.manual_seed(3)
+    ref = _engine(O.PointwiseDenoiser(O.VESampling()), dict(n_steps=2), rng="philox")
+    assert torch.equal(out, ref(x.clone(), y, noise, sig, m, tuple(times), None, 0, n_steps=2))
