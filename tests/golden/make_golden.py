@@ -194,7 +194,7 @@ def dump_node_api():
         m = (torch.rand(mshape, generator=g) > 0.6).float()
         cases["in_" + key] = m.numpy()
         cases["out_" + key] = ref.reshape_mask(m, oshape, video).contiguous().numpy()
-    np.savez_compressed(os.path.join(HERE, "reshape_mask_cases.npz"), **cases)
+    np.savez_compressed(os.path.join(HERE, "aux_reshape_mask_cases.npz"), **cases)
     with open(os.path.join(HERE, "node_api.json"), "w") as f:
         json.dump(api, f, indent=1, ensure_ascii=False, sort_keys=False)
     for n in ("comfy", "comfy.utils", "comfy.samplers", "comfy.model_base", "nodes", "latent_preview",

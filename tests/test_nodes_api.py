@@ -118,7 +118,7 @@ def test_reshape_mask_matches_reference_outputs(nodes_mod):
     src = open(os.path.join(GOLDEN_DIR, "make_golden.py")).read()
     ns = {}
     exec(src[src.index("RESHAPE_CASES = {"):src.index("def dump_node_api")], ns)
-    z = np.load(os.path.join(GOLDEN_DIR, "reshape_mask_cases.npz"))
+    z = np.load(os.path.join(GOLDEN_DIR, "aux_reshape_mask_cases.npz"))
     for key, (mshape, oshape, video) in ns["RESHAPE_CASES"].items():
         got = nodes_mod.reshape_mask(torch.from_numpy(z["in_" + key]), oshape, video)
         assert tuple(got.shape) == tuple(oshape), key
