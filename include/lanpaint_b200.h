@@ -30,8 +30,8 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 1
-#define LP_TABLE_STRIDE 24 /* floats per table row, layout below */
+#define LP_ABI_VERSION 2
+#define LP_TABLE_STRIDE 32 /* floats per table row (one 128-byte line), layout below */
 
 typedef void* lp_stream_t; /* a cudaStream_t / CUstream */
 
@@ -54,12 +54,16 @@ typedef enum lp_status {
  *   6 rep_y
  *   7 corr       audio target correction c (1 = none)         [lanpaint.py:173-180]
  *   8+8k .. 15+8k  class k: g (= A - 1/(1-abt)), dt, e_full, k_full, sd_full, e_half, k_half, sd_half
+ *   24,25      sdm[k]   = sqrt((e_half sd_half)^2 + sd_half^2): std of the two half-advance kicks a steady
+ *                         fused launch applies, merged into one Gaussian (LP_SUBSTEP_MERGE_NOISE)
+ *   26,27      sdmf[k]  = sqrt((e_half sd_full)^2 + sd_half^2): same for the FIRST|FUSE_NEXT launch
+ *   28..31     reserved (0)
  * where for an advance over h:  e = exp(-A h), k = (1-e)/A, sd = sqrt(D^2 (1-exp(-2 A h))/(2A)), D = sqrt(2)
  * (src/LanPaint/lanpaint.py:232-254), full = dt, half = dt/2.
  */
 enum {
   LP_T_CTGT = 0, LP_T_S = 1, LP_T_INVS = 2, LP_T_LAM = 3, LP_T_ONEPLAM = 4,
-  LP_T_REPN = 5, LP_T_REPY = 6, LP_T_CORR = 7, LP_T_CLS0 = 8, LP_T_CLS1 = 16,
+  LP_T_REPN = 5, LP_T_REPY = 6, LP_T_CORR = 7, LP_T_CLS0 = 8, LP_T_CLS1 = 16, LP_T_SDM = 24, LP_T_SDMF = 26,
   LP_C_G = 0, LP_C_DT = 1, LP_C_EF = 2, LP_C_KF = 3, LP_C_SF = 4, LP_C_EH = 5, LP_C_KH = 6, LP_C_SH = 7
 };
 
@@ -139,7 +143,11 @@ int lp_prologue_f32(const float* x, const float* y, const float* noise, const ui
 enum {
   LP_SUBSTEP_FIRST = 1,     /* sub-step 0: no previous C, one full-dt advance (run_overdamped, args is None) */
   LP_SUBSTEP_FUSE_NEXT = 2, /* also apply the first half-advance of the NEXT sub-step (uses the new C) */
-  LP_SUBSTEP_STORE_C = 4    /* write the new C even without FUSE_NEXT (un-fused / early-stop loops) */
+  LP_SUBSTEP_STORE_C = 4,   /* write the new C even without FUSE_NEXT (un-fused / early-stop loops) */
+  LP_SUBSTEP_MERGE_NOISE = 8 /* with FUSE_NEXT and LP_RNG_PHILOX only: the two Gaussian kicks of the launch are
+                                independent and nothing observes the state between them, so draw ONE normal with
+                                the summed variance (table sdm/sdmf).  Same Markov chain in distribution, half the
+                                RNG work; not stream-compatible with the reference, hence never used by TAPE/TORCH */
 };
 
 /* One fused Langevin launch = everything between two model calls
@@ -154,7 +162,7 @@ enum {
  * x_copy (optional) also receives the new x (the reference's
  * input_x.copy_(x), lanpaint.py:156); x0e_out (optional) receives
  * x_t + score, the LangevinState.x0 the early stopper watches.
- * Consumes 2 draws with FUSE_NEXT, else 1. */
+ * Consumes 2 draws with FUSE_NEXT (1 with MERGE_NOISE), else 1. */
 int lp_substep_f32(float* x_model, const float* x0, const float* x0_big, const float* y,
                    const uint8_t* mask, float* c_state, float* x_copy, float* x0e_out,
                    const float* table, const lp_dims* dims, const lp_rng* rng, int flags,

@@ -11,11 +11,11 @@ from typing import Optional
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "liblanpaint_b200.so")
 
-ABI_VERSION = 1
-TABLE_STRIDE = 24
+ABI_VERSION = 2
+TABLE_STRIDE = 32
 
 RNG_TAPE, RNG_PHILOX, RNG_TORCH = 0, 1, 2
-SUBSTEP_FIRST, SUBSTEP_FUSE_NEXT, SUBSTEP_STORE_C = 1, 2, 4
+SUBSTEP_FIRST, SUBSTEP_FUSE_NEXT, SUBSTEP_STORE_C, SUBSTEP_MERGE_NOISE = 1, 2, 4, 8
 
 # every symbol include/lanpaint_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = (

@@ -103,26 +103,24 @@ struct RowCoef {
   float c_tgt, S, inv_S, lam, one_plus_lam, corr;
   float g[2], dt[2], e1[2], k1[2], s1[2];  // advance #1: full dt when kFirst, else half
   float e2[2], k2[2], s2[2];               // advance #2 (only when kNext): always half
+  float sm[2];                             // merged kick of advance #1 + #2 (LP_SUBSTEP_MERGE_NOISE)
 
+  // The row is one 128-byte line: eight 128-bit read-only loads, L1-resident after the first warp.
   __device__ __forceinline__ void load(const float* __restrict__ t) {
-    c_tgt = __ldg(t + LP_T_CTGT);
-    S = __ldg(t + LP_T_S);
-    inv_S = __ldg(t + LP_T_INVS);
-    lam = __ldg(t + LP_T_LAM);
-    one_plus_lam = __ldg(t + LP_T_ONEPLAM);
-    corr = __ldg(t + LP_T_CORR);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float* c = t + LP_T_CLS0 + 8 * k;
-      g[k] = __ldg(c + LP_C_G);
-      dt[k] = __ldg(c + LP_C_DT);
-      e1[k] = __ldg(c + (kFirst ? LP_C_EF : LP_C_EH));
-      k1[k] = __ldg(c + (kFirst ? LP_C_KF : LP_C_KH));
-      s1[k] = __ldg(c + (kFirst ? LP_C_SF : LP_C_SH));
-      e2[k] = __ldg(c + LP_C_EH);
-      k2[k] = __ldg(c + LP_C_KH);
-      s2[k] = __ldg(c + LP_C_SH);
-    }
+    const float4* q = reinterpret_cast<const float4*>(t);
+    const float4 h0 = __ldg(q + 0), h1 = __ldg(q + 1);
+    const float4 a0 = __ldg(q + 2), a1 = __ldg(q + 3), b0 = __ldg(q + 4), b1 = __ldg(q + 5);
+    const float4 m = __ldg(q + 6);
+    c_tgt = h0.x; S = h0.y; inv_S = h0.z; lam = h0.w;
+    one_plus_lam = h1.x; corr = h1.w;
+    g[0] = a0.x; dt[0] = a0.y; g[1] = b0.x; dt[1] = b0.y;
+    // class row: g, dt, e_full, k_full, sd_full, e_half, k_half, sd_half
+    e1[0] = kFirst ? a0.z : a1.y; k1[0] = kFirst ? a0.w : a1.z; s1[0] = kFirst ? a1.x : a1.w;
+    e1[1] = kFirst ? b0.z : b1.y; k1[1] = kFirst ? b0.w : b1.z; s1[1] = kFirst ? b1.x : b1.w;
+    e2[0] = a1.y; k2[0] = a1.z; s2[0] = a1.w;
+    e2[1] = b1.y; k2[1] = b1.z; s2[1] = b1.w;
+    sm[0] = kFirst ? m.z : m.x;
+    sm[1] = kFirst ? m.w : m.y;
   }
 };
 
@@ -132,7 +130,7 @@ struct RowCoef {
 //   returns the new C through cnew and x_t + score through x0e
 // Reference: score_model lanpaint.py:182-184, Coef_C :217-220,
 // advance_time_overdamped :232-254, run_overdamped :274-286.
-template <bool kFirst, bool kNext>
+template <bool kFirst, bool kNext, bool kMerge = false>
 __device__ __forceinline__ void substep_element(float& x, float x0, float x0b, float y, float cprev,
                                                 bool known, float xi1, float xi2,
                                                 const RowCoef<kFirst, kNext>& t, float& cnew,
@@ -154,31 +152,49 @@ __device__ __forceinline__ void substep_element(float& x, float x0, float x0b, f
   // x_t + score: free region -> x0 ; known region -> (1+lam) y - lam x0_BIG
   const float tgt = known ? fmaf(-t.lam, x0b, t.one_plus_lam * y) : x0;
   const float cn = fmaf(t.c_tgt, tgt, g * xt);
-  if (kFirst) {
-    xt = fmaf(e1, xt, fmaf(k1, cn, s1 * xi1));
+  if (kMerge) {
+    // both kicks folded into one Gaussian of std sm (see LP_SUBSTEP_MERGE_NOISE); drift terms unchanged
+    const float sm = known ? t.sm[1] : t.sm[0];
+    if (kFirst) {
+      xt = fmaf(e1, xt, k1 * cn);
+    } else {
+      xt = fmaf(cn - cprev, dt, xt);
+      xt = fmaf(e1, xt, k1 * cprev);
+    }
+    xt = fmaf(e2, xt, fmaf(k2, cn, sm * xi1));
   } else {
-    xt = fmaf(cn - cprev, dt, xt);
-    xt = fmaf(e1, xt, fmaf(k1, cprev, s1 * xi1));  // old C on purpose (lanpaint.py:283-284)
+    if (kFirst) {
+      xt = fmaf(e1, xt, fmaf(k1, cn, s1 * xi1));
+    } else {
+      xt = fmaf(cn - cprev, dt, xt);
+      xt = fmaf(e1, xt, fmaf(k1, cprev, s1 * xi1));  // old C on purpose (lanpaint.py:283-284)
+    }
+    if (kNext) xt = fmaf(e2, xt, fmaf(k2, cn, s2 * xi2));
   }
-  if (kNext) xt = fmaf(e2, xt, fmaf(k2, cn, s2 * xi2));
   x = xt * t.S;
   cnew = cn;
   x0e = tgt;
 }
 
+// n / d for n < 2^31 without a hardware divide: q = umulhi(n, mul) >> shift (mul == 0: d == 1).
+struct FastDiv {
+  uint32_t d, mul, shift;
+  __device__ __forceinline__ uint32_t div(uint32_t n) const { return mul ? (__umulhi(n, mul) >> shift) : n; }
+};
+
 struct Geometry {
   uint32_t total;     // B * per_row
-  uint32_t per_row;   // elements per table row
-  uint32_t spatial;   // elements per channel
   uint32_t mask_row_stride;
   uint32_t mask_channel_stride;
+  FastDiv per_row;    // elements per table row
+  FastDiv spatial;    // elements per channel
 };
 
 __device__ __forceinline__ void locate(const Geometry& g, uint32_t i, uint32_t& row, uint32_t& mask_index) {
-  row = i / g.per_row;
-  const uint32_t r = i - row * g.per_row;
-  const uint32_t ch = r / g.spatial;
-  const uint32_t s = r - ch * g.spatial;
+  row = g.per_row.div(i);
+  const uint32_t r = i - row * g.per_row.d;
+  const uint32_t ch = g.spatial.div(r);
+  const uint32_t s = r - ch * g.spatial.d;
   mask_index = row * g.mask_row_stride + ch * g.mask_channel_stride + s;
 }
 
@@ -226,7 +242,10 @@ __device__ __forceinline__ void load_f(const float* p, uint32_t i, float (&v)[N]
 template <int N>
 __device__ __forceinline__ void load_f_ro(const float* __restrict__ p, uint32_t i, float (&v)[N]) {
   if (N == 4) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p + i));
+    float4 t;  // read-once stream: keep it out of L1
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                 : "l"(p + i));
     v[0] = t.x; v[1 % N] = t.y; v[2 % N] = t.z; v[3 % N] = t.w;
   } else {
     v[0] = __ldg(p + i);
@@ -251,7 +270,7 @@ __device__ __forceinline__ void load_m(const uint8_t* __restrict__ p, uint32_t i
 }
 
 // ---- TAPE / PHILOX: one N-wide vector per thread ---------------------------
-template <int N, int kRng, bool kFirst, bool kNext>
+template <int N, int kRng, bool kFirst, bool kNext, bool kMerge = false>
 __global__ void __launch_bounds__(kBlock) substep_kernel(const SubstepArgs a) {
   const uint32_t v = blockIdx.x * kBlock + threadIdx.x;
   const uint32_t i = v * N;
@@ -295,7 +314,7 @@ __global__ void __launch_bounds__(kBlock) substep_kernel(const SubstepArgs a) {
     }
     const float4 n1 = philox_normal4(seed, d0, i >> 2);
     float4 n2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (kNext) n2 = philox_normal4(seed, d1, i >> 2);
+    if (kNext && !kMerge) n2 = philox_normal4(seed, d1, i >> 2);
     if (N == 4) {
       xi1[0] = n1.x; xi1[1 % N] = n1.y; xi1[2 % N] = n1.z; xi1[3 % N] = n1.w;
       xi2[0] = n2.x; xi2[1 % N] = n2.y; xi2[2 % N] = n2.z; xi2[3 % N] = n2.w;
@@ -309,7 +328,8 @@ __global__ void __launch_bounds__(kBlock) substep_kernel(const SubstepArgs a) {
   t.load(a.table + (size_t)row * LP_TABLE_STRIDE);
 #pragma unroll
   for (int j = 0; j < N; ++j)
-    substep_element<kFirst, kNext>(x[j], x0[j], x0b[j], y[j], cp[j], known[j], xi1[j], xi2[j], t, cn[j], te[j]);
+    substep_element<kFirst, kNext, kMerge>(x[j], x0[j], x0b[j], y[j], cp[j], known[j], xi1[j], xi2[j], t, cn[j],
+                                           te[j]);
 
   store_f<N>(a.x, i, x);
   if (kNext || a.store_c) store_f<N>(a.c, i, cn);
@@ -548,6 +568,19 @@ inline int check_launch() {
   return LP_OK;
 }
 
+// Exact for every n < 2^31: with l = ceil(log2 d), mul = floor(2^(31+l)/d) + 1 < 2^32 and the error
+// n * eps / 2^(31+l) stays below 1/d.  d == 1 is flagged with mul == 0.
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f{d, 0u, 0u};
+  if (d <= 1) return f;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  const unsigned shift = 31 + l;
+  f.mul = static_cast<uint32_t>(((1ull << shift) / d) + 1);
+  f.shift = l - 1;
+  return f;
+}
+
 inline int make_geometry(const lp_dims* d, Geometry& g) {
   if (!d || d->n_rows < 0 || d->per_row <= 0 || d->spatial <= 0) return LP_ERR_INVALID;
   if (d->per_row % d->spatial != 0) return LP_ERR_INVALID;
@@ -556,8 +589,8 @@ inline int make_geometry(const lp_dims* d, Geometry& g) {
   const int64_t mask_extent = d->n_rows * d->mask_row_stride + d->per_row;  // loose upper bound
   if (total >= (int64_t(1) << 31) || mask_extent >= (int64_t(1) << 31)) return LP_ERR_UNSUPPORTED;
   g.total = static_cast<uint32_t>(total);
-  g.per_row = static_cast<uint32_t>(d->per_row);
-  g.spatial = static_cast<uint32_t>(d->spatial);
+  g.per_row = make_fastdiv(static_cast<uint32_t>(d->per_row));
+  g.spatial = make_fastdiv(static_cast<uint32_t>(d->spatial));
   g.mask_row_stride = static_cast<uint32_t>(d->mask_row_stride);
   g.mask_channel_stride = static_cast<uint32_t>(d->mask_channel_stride);
   return LP_OK;
@@ -565,7 +598,7 @@ inline int make_geometry(const lp_dims* d, Geometry& g) {
 
 // 128-bit path needs every row / channel / mask offset to stay 4-aligned.
 inline bool geometry_vec4(const Geometry& g, const uint8_t* mask) {
-  return g.per_row % 4 == 0 && g.spatial % 4 == 0 && g.mask_row_stride % 4 == 0 &&
+  return g.per_row.d % 4 == 0 && g.spatial.d % 4 == 0 && g.mask_row_stride % 4 == 0 &&
          g.mask_channel_stride % 4 == 0 && aligned4(mask);
 }
 
@@ -591,8 +624,13 @@ int torch_grid(int64_t numel, int device, int64_t* grid, uint64_t* inc) {
 }
 
 template <int N, int kRng>
-int launch_substep_vec(const SubstepArgs& a, bool first, bool next, cudaStream_t s) {
+int launch_substep_vec(const SubstepArgs& a, bool first, bool next, bool merge, cudaStream_t s) {
   const unsigned grid = blocks_for((a.g.total + N - 1) / N);
+  if (merge && kRng == LP_RNG_PHILOX) {
+    if (first) substep_kernel<N, LP_RNG_PHILOX, true, true, true><<<grid, kBlock, 0, s>>>(a);
+    else substep_kernel<N, LP_RNG_PHILOX, false, true, true><<<grid, kBlock, 0, s>>>(a);
+    return check_launch();
+  }
   if (first && next) substep_kernel<N, kRng, true, true><<<grid, kBlock, 0, s>>>(a);
   else if (first) substep_kernel<N, kRng, true, false><<<grid, kBlock, 0, s>>>(a);
   else if (next) substep_kernel<N, kRng, false, true><<<grid, kBlock, 0, s>>>(a);
@@ -656,7 +694,10 @@ extern "C" int lp_substep_f32(float* x_model, const float* x0, const float* x0_b
                               const float* table, const lp_dims* dims, const lp_rng* rng, int flags,
                               lp_stream_t stream) {
   if (!x_model || !x0 || !y || !mask || !table || !rng) return LP_ERR_INVALID;
-  if (flags & ~(LP_SUBSTEP_FIRST | LP_SUBSTEP_FUSE_NEXT | LP_SUBSTEP_STORE_C)) return LP_ERR_INVALID;
+  if (flags & ~(LP_SUBSTEP_FIRST | LP_SUBSTEP_FUSE_NEXT | LP_SUBSTEP_STORE_C | LP_SUBSTEP_MERGE_NOISE))
+    return LP_ERR_INVALID;
+  const bool merge = (flags & LP_SUBSTEP_MERGE_NOISE) != 0;
+  if (merge && (!(flags & LP_SUBSTEP_FUSE_NEXT) || rng->mode != LP_RNG_PHILOX)) return LP_ERR_INVALID;
   const int first = (flags & LP_SUBSTEP_FIRST) != 0;
   const int has_next = (flags & LP_SUBSTEP_FUSE_NEXT) != 0;
   if (!x0_big) x0_big = x0;
@@ -690,10 +731,11 @@ extern "C" int lp_substep_f32(float* x_model, const float* x0, const float* x0_b
   if (rng->mode == LP_RNG_TAPE) {
     if (!rng->tape0 || (n && !rng->tape1)) return LP_ERR_INVALID;
     v4 = v4 && aligned16(rng->tape0) && (!n || aligned16(rng->tape1));
-    return v4 ? launch_substep_vec<4, LP_RNG_TAPE>(a, f, n, s) : launch_substep_vec<1, LP_RNG_TAPE>(a, f, n, s);
+    return v4 ? launch_substep_vec<4, LP_RNG_TAPE>(a, f, n, false, s) : launch_substep_vec<1, LP_RNG_TAPE>(a, f, n, false, s);
   }
   if (rng->mode == LP_RNG_PHILOX) {
-    return v4 ? launch_substep_vec<4, LP_RNG_PHILOX>(a, f, n, s) : launch_substep_vec<1, LP_RNG_PHILOX>(a, f, n, s);
+    return v4 ? launch_substep_vec<4, LP_RNG_PHILOX>(a, f, n, merge, s)
+              : launch_substep_vec<1, LP_RNG_PHILOX>(a, f, n, merge, s);
   }
   return LP_ERR_INVALID;
 }

@@ -32,9 +32,12 @@ Advance ou_coefficients(double A, double h) {
   return a;
 }
 
-void fill_class(float* c, double A, double g, double dt) {
+void fill_class(float* c, double A, double g, double dt, float* sdm, float* sdmf) {
   const Advance full = ou_coefficients(A, dt);
   const Advance half = ou_coefficients(A, 0.5 * dt);
+  // two independent kicks sd1*xi1 then (after multiplication by e_half) sd_half*xi2 == one kick of this std
+  *sdm = static_cast<float>(std::sqrt(half.e * half.sd * half.e * half.sd + half.sd * half.sd));
+  *sdmf = static_cast<float>(std::sqrt(half.e * full.sd * half.e * full.sd + half.sd * half.sd));
   c[LP_C_G] = static_cast<float>(g);
   c[LP_C_DT] = static_cast<float>(dt);
   c[LP_C_EF] = static_cast<float>(full.e);
@@ -80,8 +83,9 @@ extern "C" int lp_build_coef_table(const double* abt, const double* ve_sigma, co
     t[LP_T_REPN] = static_cast<float>(rep_noise ? rep_noise[r] : 0.0);
     t[LP_T_REPY] = static_cast<float>(rep_y ? rep_y[r] : 1.0);
     t[LP_T_CORR] = static_cast<float>(corr ? corr[r] : 1.0);
-    fill_class(t + LP_T_CLS0, A_free, 0.0, dt_free);
-    fill_class(t + LP_T_CLS1, A_known, hp->lam * inv1m, dt_known);
+    fill_class(t + LP_T_CLS0, A_free, 0.0, dt_free, t + LP_T_SDM, t + LP_T_SDMF);
+    fill_class(t + LP_T_CLS1, A_known, hp->lam * inv1m, dt_known, t + LP_T_SDM + 1, t + LP_T_SDMF + 1);
+    for (int j = 28; j < LP_TABLE_STRIDE; ++j) t[j] = 0.f;
   }
   return LP_OK;
 }

@@ -145,6 +145,9 @@ class LanPaint:
                       independent B=1 request; uses model_sampling.noise_scaling's form)
       replace_mode    "probe" (derive the linear form of noise_scaling from a 4-point host
                       probe; falls back to "call" if it is not linear) | "call"
+      merge_noise     rng="philox" only: a fused launch applies two independent Gaussian kicks with
+                      nothing observing the state in between, so it draws one normal with the summed
+                      variance (identical chain in distribution, half the RNG work)
       cuda_graph      False | True: capture the whole outer step (model calls included) into one
                       CUDA graph per (shape, sub-step count) and replay it; falls back to eager
                       launches if the model is not capture-safe
@@ -152,7 +155,8 @@ class LanPaint:
 
     def __init__(self, Model, NSteps, Friction, Lambda, Beta, StepSize, IS_FLUX=False, IS_FLOW=False,
                  EarlyStopThreshold=0.0, EarlyStopPatience=1, EarlyStopHook=None, MinStepFrac=0.0, *,
-                 rng="torch", batched_replace="reference", replace_mode="probe", cuda_graph=False):
+                 rng="torch", batched_replace="reference", replace_mode="probe", cuda_graph=False,
+                 merge_noise=True):
         self.n_steps = NSteps
         self.chara_lamb = Lambda
         self.IS_FLUX = IS_FLUX
@@ -170,6 +174,7 @@ class LanPaint:
         self.batched_replace = batched_replace
         self.replace_mode = replace_mode
         self.cuda_graph = cuda_graph
+        self.merge_noise = merge_noise
         self._graphs = {}
         self._graph_statics = {}
         # statistics a caller (bench, tests) can read back
@@ -389,7 +394,10 @@ class LanPaint:
             if stopper is None:
                 # fused: post-model half of sub-step i + pre-model half of sub-step i+1
                 flags = (F.SUBSTEP_FIRST if first else 0) | (F.SUBSTEP_FUSE_NEXT if has_next else 0)
-                r = plan.rng_struct(2 if has_next else 1, rng_state)
+                merge = has_next and plan.mode == F.RNG_PHILOX and self.merge_noise
+                if merge:  # one Gaussian with the summed variance instead of two (philox stream only)
+                    flags |= F.SUBSTEP_MERGE_NOISE
+                r = plan.rng_struct(2 if (has_next and not merge) else 1, rng_state)
                 ev = self._event_pair(flags) if self.kernel_timer is not None else None
                 rc = lib.lp_substep_f32(_P(xm.data_ptr()), _P(x0.data_ptr()), _P(x0b.data_ptr()),
                                         _P(y.data_ptr()), _P(pm.data.data_ptr()), _P(cbuf.data_ptr()), None, None,
@@ -466,7 +474,7 @@ class LanPaint:
         g["graph"].replay()
         self.launches += g["launches"]
         self.model_calls += g["model_calls"]
-        plan.consume(2 * active - 1 if active > 0 else 0)
+        plan.consume(g["draws"])
         x.copy_(st["x"])            # the in-place contract of lanpaint.py:156
         return g["out"].clone()     # a fresh tensor, like the reference returns
 
@@ -527,7 +535,7 @@ class LanPaint:
             self.kernel_timer = timer
             return None
         self.kernel_timer = timer
-        g = {"graph": graph, "params": params, "out": out,
+        g = {"graph": graph, "params": params, "out": out, "draws": rel.used,
              "launches": self.launches - counts[0], "model_calls": self.model_calls - counts[1]}
         self.launches, self.model_calls = counts
         self._graphs[key] = g

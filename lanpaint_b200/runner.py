@@ -134,3 +134,165 @@ def euler_inpaint(engine, latent_image: torch.Tensor, noise: torch.Tensor, mask,
         x_out.copy_(x, non_blocking=True)
         return x_out
     return x
+
+
+def time_steady_substep(engine, latent_image: torch.Tensor, mask, sigma: float, launches: int = 53,
+                        repeats: int = 20, flow: bool = False):
+    """Roofline probe: `launches` steady fused sub-step launches (flags = FUSE_NEXT, the kernel that
+    dominates a job) back to back on job-shaped operands, between two CUDA events on the launching
+    stream, `repeats` times.  Returns the list of per-launch durations in microseconds (one per repeat).
+
+    The operands are the real ones of a job (same shapes, mask, coefficient table, RNG mode); the
+    launches are identical to those `LanPaint._launch_sequence` issues, minus the model call between them."""
+    import ctypes as C
+    import numpy as np
+    from .engine import PackedMask, _DrawPlan, pack_mask
+    from .schedule import Hyper, build_table
+    lib = _native.load()
+    dev = latent_image.device
+    B = latent_image.shape[0]
+    x = torch.randn_like(latent_image)
+    heads = engine.inner_model(x, torch.full((B,), sigma, device=dev))
+    x0, x0b = engine.unpack_model_output(heads)
+    x0, x0b = x0.clone(), x0b.clone()
+    cbuf = torch.randn_like(x)
+    pm = mask if isinstance(mask, PackedMask) else pack_mask(mask, x)
+    s = torch.full((B,), sigma, dtype=torch.float32)
+    ve, abt, _ = times_from_sigma(s, flow)
+    hp = Hyper(engine.step_size, engine.chara_lamb, engine.chara_beta, engine.min_step_frac, flow)
+    tab = torch.from_numpy(build_table(abt.numpy(), ve.numpy(), hp)).to(dev)
+    per_row = x.numel() // B
+    spatial = int(np.prod(x.shape[2:]))
+    dims = _native.Dims(B, per_row, spatial, pm.row_stride, pm.channel_stride)
+    plan = _DrawPlan(engine.rng, x, launches + 1)
+    merge = plan.mode == _native.RNG_PHILOX and engine.merge_noise
+    flags = _native.SUBSTEP_FUSE_NEXT | (_native.SUBSTEP_MERGE_NOISE if merge else 0)
+    P = C.c_void_p
+    stream = P(torch.cuda.current_stream(dev).cuda_stream)
+
+    def burst():
+        for _ in range(launches):
+            r = plan.rng_struct(1 if merge else 2)
+            rc = lib.lp_substep_f32(P(x.data_ptr()), P(x0.data_ptr()), P(x0b.data_ptr()), P(latent_image.data_ptr()),
+                                    P(pm.data.data_ptr()), P(cbuf.data_ptr()), None, None, P(tab.data_ptr()),
+                                    C.byref(dims), C.byref(r), flags, stream)
+            _native.check(rc, "lp_substep_f32")
+
+    for _ in range(3):
+        burst()
+    torch.cuda.synchronize(dev)
+    out = []
+    for _ in range(repeats):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        burst()
+        e1.record()
+        e1.synchronize()
+        out.append(1e3 * e0.elapsed_time(e1) / launches)
+    return out
+
+
+class GraphedJob:
+    """A whole inpaint job -- initial noise_scaling, every outer step (prologue, model calls, fused
+    sub-steps, epilogue) and the Euler updates between them -- captured ONCE as a single CUDA graph and
+    replayed per batch of requests.  Everything sigma-dependent is a device constant computed at
+    construction (one coefficient table per outer step), so a replay costs one 16-byte H2D copy (the RNG
+    position) plus the copies of the request's own inputs.  This is the serving configuration: fixed
+    schedule, fixed batch shape, a stream of request batches.
+
+    Semantics are exactly `euler_inpaint(engine, ...)` (asserted bit-for-bit by the tests)."""
+
+    def __init__(self, engine, sched: HostSchedule, shape, device, flow: bool = False):
+        import numpy as np
+        from .engine import _DrawPlan
+        from .schedule import Hyper, build_table, mean_half_dt
+        if engine.rng not in ("philox", "torch"):
+            raise ValueError("GraphedJob needs an in-kernel RNG mode ('philox' or 'torch')")
+        self.engine, self.sched, self.flow = engine, sched, flow
+        self.device = torch.device(device)
+        self.shape = tuple(shape)
+        B = self.shape[0]
+        dev = self.device
+        mk = lambda: torch.empty(self.shape, dtype=torch.float32, device=dev)
+        self.x, self.y, self.noise, self.c, self.out = mk(), mk(), mk(), mk(), mk()
+        self.mask = None
+        hyper = Hyper(engine.step_size, engine.chara_lamb, engine.chara_beta, engine.min_step_frac, flow)
+        tabs, tms, sgs, self.active = [], [], [], []
+        for st in sched.steps:
+            ve, abt, flow_t = (t.numpy() for t in st.times)
+            sig = st.sigma_t.numpy()
+            form = engine._replace_form(sig, st.sigma_t.numel() == 1, B, engine.replace_mode, engine.batched_replace)
+            if form is None:
+                raise ValueError("model_sampling.noise_scaling is not a linear form; GraphedJob cannot precompute it")
+            tabs.append(build_table(abt, ve, hyper, form[0], form[1]))
+            tms.append(flow_t if flow else ve)
+            sgs.append(sig)
+            self.active.append(st.n_inner if mean_half_dt(abt, hyper) > 0.0 else 0)
+        self.tables = torch.from_numpy(np.stack(tabs)).to(dev)
+        self.t_model = torch.from_numpy(np.stack(tms).astype(np.float32)).to(dev)
+        self.sigma = torch.from_numpy(np.stack(sgs).astype(np.float32)).to(dev)
+        self.sigma0 = torch.tensor(float(sched.sigmas[0]), device=dev)
+        self.rng_state = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.graph = None
+        self.draws = 0
+        self.launches = 0
+        self.model_calls = 0
+        self._plan_cls = _DrawPlan
+
+    def _body(self, pm, dims, plan):
+        eng = self.engine
+        sampling = eng.inner_model.inner_model.model_sampling
+        self.x.copy_(sampling.noise_scaling(self.sigma0, self.noise, self.y))
+        state = self.rng_state.data_ptr()
+        for i, st in enumerate(self.sched.steps):
+            eng._launch_sequence(self.x, self.y, self.noise, pm, dims, self.tables[i], self.t_model[i], self.sigma[i],
+                                 self.c, self.out, self.active[i], plan, False, None, 0, None, state)
+            self.x.add_(self.x - self.out, alpha=(st.sigma_next - st.sigma) / st.sigma)
+
+    def _capture(self, pm):
+        import numpy as np
+        eng = self.engine
+        B = self.shape[0]
+        dims = _native.Dims(B, self.x.numel() // B, int(np.prod(self.shape[2:])), pm.row_stride, pm.channel_stride)
+        plan = self._plan_cls(eng.rng, self.x, 1).relative()
+        counts = (eng.launches, eng.model_calls)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self._body(pm, dims, plan)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        plan.reset()
+        eng.launches, eng.model_calls = counts
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self._body(pm, dims, plan)
+        self.graph, self.draws = graph, plan.used
+        self.launches, self.model_calls = eng.launches - counts[0], eng.model_calls - counts[1]
+        eng.launches, eng.model_calls = counts
+
+    def run(self, latent_image: torch.Tensor, noise: torch.Tensor, mask, x_out: Optional[torch.Tensor] = None):
+        import numpy as np
+        from .engine import PackedMask, pack_mask
+        eng = self.engine
+        self.y.copy_(latent_image, non_blocking=True)
+        self.noise.copy_(noise, non_blocking=True)
+        pm = mask if isinstance(mask, PackedMask) else pack_mask(mask, self.x)
+        if self.mask is None or self.mask.data.shape != pm.data.shape or (
+                self.mask.row_stride, self.mask.channel_stride) != (pm.row_stride, pm.channel_stride):
+            self.mask = PackedMask(torch.empty_like(pm.data), pm.row_stride, pm.channel_stride)
+            self.graph = None
+        self.mask.data.copy_(pm.data, non_blocking=True)
+        if self.graph is None:
+            self._capture(self.mask)
+        plan = self._plan_cls(eng.rng, self.x, 1)
+        self.rng_state.copy_(torch.from_numpy(plan.state_words().view(np.int64)))
+        self.graph.replay()
+        plan.consume(self.draws)
+        plan.finish()
+        eng.launches += self.launches
+        eng.model_calls += self.model_calls
+        eng.substeps_done += self.sched.substeps
+        if x_out is not None:
+            x_out.copy_(self.x, non_blocking=True)
+            return x_out
+        return self.x.clone()

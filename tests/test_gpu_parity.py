@@ -409,3 +409,92 @@ def test_graph_capture_failure_falls_back_to_eager(cuda_device):
     torch.manual_seed(3)
     ref = _engine(O.PointwiseDenoiser(O.VESampling()), dict(n_steps=2), rng="philox")
     assert torch.equal(out, ref(x.clone(), y, noise, sig, m, tuple(times), None, 0, n_steps=2))
+
+
+# ----------------------------------------------------------------------------
+# 6. merged Gaussian kick (LP_SUBSTEP_MERGE_NOISE, philox stream only)
+# ----------------------------------------------------------------------------
+def _raw_substep(lib, x, x0, x0b, y, m8, c, tab, dims, flags, seed=5, draw=0):
+    from lanpaint_b200 import _native
+    P = C.c_void_p
+    r = _native.Rng(mode=_native.RNG_PHILOX, seed=seed, draw0=draw, draw1=draw + 1)
+    rc = lib.lp_substep_f32(P(x.data_ptr()), P(x0.data_ptr()), P(x0b.data_ptr()), P(y.data_ptr()), P(m8.data_ptr()),
+                            P(c.data_ptr()), None, None, P(tab.data_ptr()), C.byref(dims), C.byref(r), flags,
+                            P(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, rc
+
+
+@pytest.mark.parametrize("first", [0, 1])
+def test_merged_noise_same_drift_and_same_variance(first, cuda_device):
+    from lanpaint_b200 import _native
+    from lanpaint_b200.schedule import Hyper, build_table
+    lib = _native.load()
+    dev = cuda_device
+    B, Cc, S = 2, 4, 1 << 16
+    sig = torch.tensor([0.8, 4.0])
+    ve, abt, _ = O.times_from_sigma(sig, False)
+    tab_np = build_table(abt.numpy(), ve.numpy(), Hyper(0.2, 5.0, 1.0, 1.0, False))
+    dims = _native.Dims(B, Cc * S, S, S, 0)
+    m8 = (torch.rand(B, 1, S, device=dev) < 0.5).to(torch.uint8)
+    base = [torch.randn(B, Cc, S, device=dev) for _ in range(5)]
+    F2, FM = 2 | first, 2 | 8 | first
+
+    # (a) with every kick std zeroed, the merged and the two-draw kernels are the same arithmetic
+    quiet = tab_np.copy()
+    quiet[:, [8 + 4, 8 + 7, 16 + 4, 16 + 7, 24, 25, 26, 27]] = 0.0
+    tq = torch.from_numpy(quiet).to(dev)
+    outs = []
+    for flags in (F2, FM):
+        x, x0, x0b, y, c = (t.clone() for t in base)
+        _raw_substep(lib, x, x0, x0b, y, m8, c, tq, dims, flags)
+        outs.append((x, c))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+    # (b) with constant operands the output is (constant + kick): its per-class variance must agree
+    tab = torch.from_numpy(tab_np).to(dev)
+    res = []
+    for flags in (F2, FM):
+        x, x0, x0b, y, c = (torch.full((B, Cc, S), v, device=dev) for v in (0.3, -0.2, 0.5, 0.1, 0.05))
+        _raw_substep(lib, x, x0, x0b, y, m8, c, tab, dims, flags)
+        res.append(x)
+    known = m8.bool().expand(B, Cc, S)
+    for b in range(B):
+        for cls in (known[b], ~known[b]):
+            v2, vm = res[0][b][cls].var().item(), res[1][b][cls].var().item()
+            m2, mm = res[0][b][cls].mean().item(), res[1][b][cls].mean().item()
+            assert abs(vm / v2 - 1.0) < 0.03, (b, v2, vm)
+            assert abs(mm - m2) < 4.0 * (v2 / cls.sum().item()) ** 0.5 + 1e-4
+    # the ABI refuses the flag where it would break stream parity
+    x, x0, x0b, y, c = (t.clone() for t in base)
+    P = C.c_void_p
+    r = _native.Rng(mode=_native.RNG_TORCH, seed=1, draw0=0, draw1=4)
+    assert lib.lp_substep_f32(P(x.data_ptr()), P(x0.data_ptr()), P(x0b.data_ptr()), P(y.data_ptr()), P(m8.data_ptr()),
+                              P(c.data_ptr()), None, None, P(tab.data_ptr()), C.byref(dims), C.byref(r), FM, None) == 1
+
+
+@pytest.mark.parametrize("rng", ["philox", "torch"])
+def test_whole_job_graph_equals_step_by_step(rng, cuda_device):
+    """runner.GraphedJob (one CUDA graph for the 20-step job) == euler_inpaint with eager launches."""
+    from lanpaint_b200.runner import GraphedJob, HostSchedule, SynthDenoiser, VESampling, euler_inpaint, karras_sigmas
+    dev = cuda_device
+    shape = (3, 4, 32, 32)
+    _, y, noise, m = synth_inputs(shape, seed=8, device=dev)
+    sched = HostSchedule(karras_sigmas(20), 3, 5)
+    assert sched.substeps == 53 and sched.model_calls == 73
+
+    def engine():
+        return _engine(SynthDenoiser(VESampling()), dict(n_steps=5), rng=rng, batched_replace="per_sample")
+
+    torch.manual_seed(4)
+    e1 = engine()
+    want = euler_inpaint(e1, y, noise, m, sched)
+    off1 = torch.cuda.default_generators[dev.index].get_offset()
+    torch.manual_seed(4)
+    e2 = engine()
+    job = GraphedJob(e2, sched, shape, dev)
+    got = job.run(y, noise, m)
+    off2 = torch.cuda.default_generators[dev.index].get_offset()
+    assert torch.equal(got, want) and off1 == off2
+    assert e2.model_calls == e1.model_calls == 73 and e2.substeps_done == 53
+    again = job.run(y, noise, m)          # a second request batch: fresh noise, same graph
+    assert not torch.equal(again, got) and torch.isfinite(again).all()
