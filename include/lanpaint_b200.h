@@ -179,6 +179,17 @@ int lp_advance_f32(float* x_model, const float* c_state, const uint8_t* mask, co
 int lp_epilogue_f32(const float* model_out, const float* y, const uint8_t* mask, float* out,
                     const lp_dims* dims, lp_stream_t stream);
 
+/* Early-stop statistics (LanPaintEarlyStopper, src/LanPaint/earlystop.py:32-55,238-313):
+ *   sums[0] = sum over elements with mask == 0 (the inpaint weight)  of (scale*(a-b))^2
+ *   sums[1] = sum over elements with ring != 0 (4-neighbour boundary) of (scale*(a-b))^2
+ * i.e. the numerators of _weighted_mse for the inpaint and boundary-ring weights; the denominators are
+ * constants of the mask.  ring may be NULL (sums[1] = 0); table may be NULL (scale = 1), otherwise
+ * scale = inv_S of the row, which turns a model-space difference into the VP-space one the reference
+ * measures on x_t.  ring uses the mask's layout/strides.  sums: 2 doubles on the device, zeroed by the call.
+ * Warp-shuffle + one atomicAdd(double) per block per sum. */
+int lp_stop_stats_f32(const float* a, const float* b, const uint8_t* mask, const uint8_t* ring,
+                      const float* table, const lp_dims* dims, double* sums, lp_stream_t stream);
+
 /* ---- device: utilities (tests, bench) ---------------------------------- */
 /* out[i] ~ N(0,1) with the given rng (PHILOX or TORCH; draw0 only). */
 int lp_fill_normal_f32(float* out, int64_t n, const lp_rng* rng, lp_stream_t stream);

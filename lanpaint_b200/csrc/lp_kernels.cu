@@ -453,6 +453,73 @@ __global__ void __launch_bounds__(kBlock) advance_torch_kernel(const AdvanceArgs
   }
 }
 
+// ---- early-stop statistics: two masked sums of squared differences ---------------
+// Grid-stride over float4 groups; per-thread partials -> warp shuffle -> one smem slot per warp ->
+// one atomicAdd(double) per block per sum (earlystop.py:51-55 _weighted_mse numerators).
+struct StatsArgs {
+  const float* a;
+  const float* b;
+  const uint8_t* mask;
+  const uint8_t* ring;
+  const float* table;
+  double* sums;
+  Geometry g;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int N>
+__global__ void __launch_bounds__(kBlock) stop_stats_kernel(const StatsArgs s) {
+  float acc_in = 0.f, acc_ring = 0.f;
+  const uint32_t stride = gridDim.x * kBlock * N;
+  for (uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N; i < s.g.total; i += stride) {
+    uint32_t row, mi;
+    locate(s.g, i, row, mi);
+    float av[N], bv[N];
+    bool known[N], on_ring[N];
+    load_f_ro<N>(s.a, i, av);
+    load_f_ro<N>(s.b, i, bv);
+    load_m<N>(s.mask, mi, known);
+    if (s.ring) {
+      load_m<N>(s.ring, mi, on_ring);
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) on_ring[j] = false;
+    }
+    const float scale = s.table ? __ldg(s.table + (size_t)row * LP_TABLE_STRIDE + LP_T_INVS) : 1.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const float d = (av[j] - bv[j]) * scale;
+      const float d2 = d * d;
+      acc_in += known[j] ? 0.f : d2;
+      acc_ring += on_ring[j] ? d2 : 0.f;
+    }
+  }
+  __shared__ float part[2][kBlock / 32];
+  acc_in = warp_sum(acc_in);
+  acc_ring = warp_sum(acc_ring);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    part[0][w] = acc_in;
+    part[1][w] = acc_ring;
+  }
+  __syncthreads();
+  if (w == 0) {
+    float u = lane < kBlock / 32 ? part[0][lane] : 0.f;
+    float v = lane < kBlock / 32 ? part[1][lane] : 0.f;
+    u = warp_sum(u);
+    v = warp_sum(v);
+    if (lane == 0) {
+      atomicAdd(s.sums + 0, (double)u);
+      atomicAdd(s.sums + 1, (double)v);
+    }
+  }
+}
+
 // ---- prologue / epilogue / utilities ----------------------------------------
 template <int N>
 __global__ void __launch_bounds__(kBlock) prologue_kernel(const float* x, const float* __restrict__ y,
@@ -775,6 +842,28 @@ extern "C" int lp_epilogue_f32(const float* model_out, const float* y, const uin
   const bool v4 = geometry_vec4(g, mask) && aligned16(model_out) && aligned16(y) && aligned16(out);
   if (v4) epilogue_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(model_out, y, mask, out, g);
   else epilogue_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(model_out, y, mask, out, g);
+  return check_launch();
+}
+
+extern "C" int lp_stop_stats_f32(const float* a, const float* b, const uint8_t* mask, const uint8_t* ring,
+                                 const float* table, const lp_dims* dims, double* sums, lp_stream_t stream) {
+  if (!a || !b || !mask || !sums) return LP_ERR_INVALID;
+  StatsArgs s;
+  if (int rc = make_geometry(dims, s.g)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(sums, 0, 2 * sizeof(double), st) != cudaSuccess) return check_launch() ? LP_ERR_CUDA : LP_ERR_CUDA;
+  if (s.g.total == 0) return LP_OK;
+  s.a = a; s.b = b; s.mask = mask; s.ring = ring; s.table = table; s.sums = sums;
+  int sms = 148;
+  int device = 0;
+  if (cudaGetDevice(&device) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  const bool v4 = geometry_vec4(s.g, mask) && aligned16(a) && aligned16(b) && (!ring || aligned4(ring));
+  const uint32_t groups = v4 ? s.g.total / 4 : s.g.total;
+  unsigned grid = blocks_for(groups);
+  const unsigned cap = (unsigned)sms * 8;  // persistent-sized: 8 CTAs of 256 threads per SM
+  if (grid > cap) grid = cap;
+  if (v4) stop_stats_kernel<4><<<grid, kBlock, 0, st>>>(s);
+  else stop_stats_kernel<1><<<grid, kBlock, 0, st>>>(s);
   return check_launch();
 }
 

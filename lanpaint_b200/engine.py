@@ -298,8 +298,6 @@ class LanPaint:
         flow = bool(IS_FLUX or IS_FLOW)
         if self.audio_indicator is not None and self.current_times_audio is not None:
             return self._av_call(x, sigma, latent_mask, current_times, n_steps, model_options, seed, flow, opts)
-        stopper = self._make_stopper(model_options, latent_mask, current_times[1])
-
         input_x = x
         B = x.shape[0]
         per_row = x.numel() // B
@@ -329,6 +327,7 @@ class LanPaint:
             self._mask_cache.put(latent_mask, pm)
             self.launches += 1
         dims = _native.Dims(B, per_row, spatial, pm.row_stride, pm.channel_stride)
+        stopper = self._make_stopper(model_options, pm, x, abt_h, dims)
 
         scalar_sigma = sigma.numel() == 1
         form = self._replace_form(sigma_h, scalar_sigma, B, rmode, batched)
@@ -384,13 +383,14 @@ class LanPaint:
         self.launches += 1
         done = 0
         for i in range(active):
-            heads = self.inner_model(xm, t_model, model_options=model_options, seed=seed)
-            self.model_calls += 1
-            h0, h1 = self.unpack_model_output(heads)
-            x0 = _as_operand(h0, xm)
-            x0b = x0 if h1 is h0 else _as_operand(h1, xm)
             first = i == 0
             has_next = i + 1 < active
+            self.model_calls += 1
+            if stopper is None or first:
+                heads = self.inner_model(xm, t_model, model_options=model_options, seed=seed)
+                h0, h1 = self.unpack_model_output(heads)
+                x0 = _as_operand(h0, xm)
+                x0b = x0 if h1 is h0 else _as_operand(h1, xm)
             if stopper is None:
                 # fused: post-model half of sub-step i + pre-model half of sub-step i+1
                 flags = (F.SUBSTEP_FIRST if first else 0) | (F.SUBSTEP_FUSE_NEXT if has_next else 0)
@@ -408,8 +408,22 @@ class LanPaint:
                 self.launches += 1
                 done += 1
                 continue
-            # early-stop loop: the decision to stop after sub-step i must be taken before the
-            # first half-advance of sub-step i+1 is applied, so that half runs as its own launch
+            # early-stop loop (lanpaint.py:116-142): the decision to stop after sub-step i must be taken
+            # before the first half-advance of sub-step i+1 is applied, so that half is its own launch
+            if first and stopper is not None:
+                x_before = xm.clone()          # state before sub-step 0 (its check has no previous x0)
+                x0e_prev = None
+            custom_prev = xm.clone() if stopper.has_custom_distance_fn else None
+            if not first:
+                r = plan.rng_struct(1, rng_state)
+                rc = lib.lp_advance_f32(_P(xm.data_ptr()), _P(cbuf.data_ptr()), _P(pm.data.data_ptr()),
+                                        _P(tab.data_ptr()), C.byref(dims), C.byref(r), 1, stream)
+                _native.check(rc, "lp_advance_f32")
+                self.launches += 1
+                heads = self.inner_model(xm, t_model, model_options=model_options, seed=seed)
+                h0, h1 = self.unpack_model_output(heads)
+                x0 = _as_operand(h0, xm)
+                x0b = x0 if h1 is h0 else _as_operand(h1, xm)
             flags = (F.SUBSTEP_FIRST if first else 0) | F.SUBSTEP_STORE_C
             x0e = stopper.next_x0e_buffer(xm)
             r = plan.rng_struct(1, rng_state)
@@ -419,14 +433,16 @@ class LanPaint:
             _native.check(rc, "lp_substep_f32")
             self.launches += 1
             done += 1
-            if stopper.step(i, active, xm, cbuf, x0e, seed):
+            inv_s = tab[:, _native.T_INVS].reshape((-1,) + (1,) * (xm.ndim - 1))
+            ctx = {"step": i, "steps_done": i + 1, "n_steps": active, "mask": pm, "latent_image": y,
+                   "current_times": None, "seed": seed}
+            stop = stopper.step(i=i, n_steps=active, x_before=x_before if first else None, x_after=xm,
+                                x0_prev=x0e_prev, x0_cur=x0e, table=tab,
+                                custom_prev=(lambda: custom_prev * inv_s) if custom_prev is not None else None,
+                                custom_cur=(lambda: xm * inv_s) if custom_prev is not None else None, ctx=ctx)
+            x0e_prev = x0e
+            if stop:
                 break
-            if has_next:
-                r = plan.rng_struct(1, rng_state)
-                rc = lib.lp_advance_f32(_P(xm.data_ptr()), _P(cbuf.data_ptr()), _P(pm.data.data_ptr()),
-                                        _P(tab.data_ptr()), C.byref(dims), C.byref(r), 1, stream)
-                _native.check(rc, "lp_advance_f32")
-                self.launches += 1
 
         # final denoise + known-region paste (lanpaint.py:151-157)
         out_heads = self.inner_model(xm, sigma_dev, model_options=model_options, seed=seed)
@@ -531,6 +547,7 @@ class LanPaint:
         except Exception as e:  # capture-unsafe model: run eagerly instead, say so once
             import warnings
             warnings.warn(f"lanpaint_b200: CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly")
+            _repair_generator_after_failed_capture(dev)
             self.launches, self.model_calls = counts
             self.kernel_timer = timer
             return None
@@ -547,15 +564,34 @@ class LanPaint:
         self.kernel_timer.append((flags, a, b))
         return a, b
 
-    def _make_stopper(self, model_options, latent_mask, abt):
+    def _make_stopper(self, model_options, pm, like, abt_h, dims):
         semantic = model_options.get("lanpaint_semantic_stop") if isinstance(model_options, dict) else None
         if not (float(self.early_stop_threshold or 0.0) > 0.0 or isinstance(semantic, dict)):
             return None
-        raise NotImplementedError("inner-loop early stop is not built yet (SURVEY 8f rank 2); "
-                                  "the nodes always pass threshold 0.0")
+        from .earlystop import make_stopper
+        return make_stopper(model_options=model_options, default_threshold=self.early_stop_threshold,
+                            default_patience=self.early_stop_patience, default_distance_fn=self.early_stop_hook,
+                            packed_mask=pm, like=like, abt_mean=float(np.float32(abt_h.astype(np.float32).mean())),
+                            dims=dims)
 
     def _av_call(self, *a, **k):
         raise NotImplementedError("MiniMax-H3 per-row audio schedule is not built yet (SURVEY 8f rank 4)")
+
+
+def _repair_generator_after_failed_capture(dev: torch.device) -> None:
+    """A capture that dies between capture_begin and capture_end leaves torch's default CUDA generator
+    flagged as "capturing" (every later torch.rand* then raises "Offset increment outside graph
+    capture").  Swapping in a cloned state object clears the flag and keeps seed and offset."""
+    try:
+        torch.cuda.synchronize(dev)
+    except Exception:
+        pass
+    try:
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        gen = torch.cuda.default_generators[idx]
+        gen.graphsafe_set_state(gen.clone_state())
+    except Exception:
+        pass
 
 
 def _as_operand(t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:

@@ -205,3 +205,61 @@ def dump_node_api():
 
 if __name__ == "__main__" and "--api" in sys.argv:
     dump_node_api()
+
+
+# --------------------------------------------------------------------------------------------
+# early-stop goldens: the reference's LanPaintEarlyStopper driven through LanPaint.__call__
+# --------------------------------------------------------------------------------------------
+def _custom_distance(prev, cur, ctx):
+    return ((cur - prev) ** 2).mean()
+
+
+EARLYSTOP_CASES = [
+    dict(name="aux_es_midway", sigma=0.3, stop={"threshold": 0.3, "patience": 2}, n=10),
+    dict(name="aux_es_immediate", sigma=1.0, stop={"threshold": 1e3, "patience": 1}, n=10),
+    dict(name="aux_es_never", sigma=2.0, stop={"threshold": 1e-9, "patience": 1}, n=6),
+    dict(name="aux_es_min_steps_legacy", sigma=1.0, stop={"threshold": 1e3, "patience": 1, "min_steps": 4}, n=10),
+    dict(name="aux_es_custom_fn", sigma=1.0, stop={"threshold": 0.5, "patience": 1, "distance_fn": "mean_sq_xt"}, n=10),
+    dict(name="aux_es_ctor_threshold", sigma=0.3, stop=None, ctor_threshold=0.26, ctor_patience=1, n=10),
+]
+
+
+def dump_earlystop():
+    torch.set_num_threads(1)
+    for c in EARLYSTOP_CASES:
+        g = torch.Generator().manual_seed(11)
+        shape = (1, 4, 16, 16)
+        x = torch.randn(shape, generator=g)
+        y = torch.randn(shape, generator=g)
+        noise = torch.randn(shape, generator=g)
+        mask = (torch.rand((1, 1, 16, 16), generator=g) < 0.5).float().expand(shape).contiguous()
+        sigma = torch.tensor([c["sigma"]])
+        times = O.times_from_sigma(sigma, False)
+        tape = O.NoiseTape(generator=torch.Generator().manual_seed(2))
+        model = make_model("two_heads", False)
+        eng = RefEngine(model, NSteps=c["n"], Friction=15.0, Lambda=5.0, Beta=1.0, StepSize=0.2, MinStepFrac=1.0,
+                        EarlyStopThreshold=c.get("ctor_threshold", 0.0), EarlyStopPatience=c.get("ctor_patience", 1))
+        trace = []
+        mo = {"lanpaint_semantic_trace": trace, "bench_case_id": c["name"], "bench_outer_step": 3, "bench_timestep": 0.5}
+        if c["stop"] is not None:
+            stop = dict(c["stop"])
+            if stop.get("distance_fn") == "mean_sq_xt":
+                stop["distance_fn"] = _custom_distance
+            mo["lanpaint_semantic_stop"] = stop
+        x_ref = x.clone()
+        with mock.patch.object(torch, "randn_like", tape):
+            out = eng(x_ref, y, noise, sigma, mask, tuple(times), model_options=mo, seed=0, n_steps=c["n"])
+        meta = dict(name=c["name"], n_steps=c["n"], stop=c["stop"], ctor_threshold=c.get("ctor_threshold", 0.0),
+                    ctor_patience=c.get("ctor_patience", 1), trace=trace, model_calls=model.calls,
+                    n_draws=len(tape.recorded))
+        print(f"{c['name']:28s} sub-steps run {len(trace):2d}/{c['n']} model calls {model.calls:2d} "
+              f"dists {[round(t['dist'], 4) for t in trace][:6]}")
+        np.savez_compressed(os.path.join(HERE, c["name"] + ".npz"), x=x.numpy(), y=y.numpy(), noise=noise.numpy(),
+                            sigma=sigma.numpy(), mask=mask[:, :1].numpy().astype(np.uint8), ve=times.ve_sigma.numpy(),
+                            abt=times.abt.numpy(), flow_t=times.flow_t.numpy(),
+                            tape=np.stack([d.numpy() for d in tape.recorded]), out=out.numpy(), x_new=x_ref.numpy(),
+                            meta=np.array(json.dumps(meta)))
+
+
+if __name__ == "__main__" and "--earlystop" in sys.argv:
+    dump_earlystop()

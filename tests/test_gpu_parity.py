@@ -409,6 +409,8 @@ def test_graph_capture_failure_falls_back_to_eager(cuda_device):
     torch.manual_seed(3)
     ref = _engine(O.PointwiseDenoiser(O.VESampling()), dict(n_steps=2), rng="philox")
     assert torch.equal(out, ref(x.clone(), y, noise, sig, m, tuple(times), None, 0, n_steps=2))
+    # the aborted capture must not leave torch's generator unusable
+    assert torch.isfinite(torch.rand(8, device=dev)).all() and torch.isfinite(torch.randn(8, device=dev)).all()
 
 
 # ----------------------------------------------------------------------------
