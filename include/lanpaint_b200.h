@@ -179,6 +179,14 @@ int lp_advance_f32(float* x_model, const float* c_state, const uint8_t* mask, co
 int lp_epilogue_f32(const float* model_out, const float* y, const uint8_t* mask, float* out,
                     const lp_dims* dims, lp_stream_t stream);
 
+/* lp_epilogue_f32 fused with the update k-diffusion's Euler sampler applies right after it
+ * (sample_euler: d = (x - denoised)/sigma; x = x + d*(sigma_next - sigma)), for hosts that own the
+ * sampler loop:
+ *   out = mask ? y : model_out ;  x = x + (x - out) * euler_coef      euler_coef = (sigma_next - sigma)/sigma
+ * x_inout is the model-space state lp_substep_f32 left behind (the rewritten sampler x). */
+int lp_epilogue_euler_f32(const float* model_out, const float* y, const uint8_t* mask, float* x_inout,
+                          float* out, float euler_coef, const lp_dims* dims, lp_stream_t stream);
+
 /* Early-stop statistics (LanPaintEarlyStopper, src/LanPaint/earlystop.py:32-55,238-313):
  *   sums[0] = sum over elements with mask == 0 (the inpaint weight)  of (scale*(a-b))^2
  *   sums[1] = sum over elements with ring != 0 (4-neighbour boundary) of (scale*(a-b))^2

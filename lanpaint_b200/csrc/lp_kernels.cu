@@ -269,16 +269,13 @@ __device__ __forceinline__ void load_m(const uint8_t* __restrict__ p, uint32_t i
   }
 }
 
-// ---- TAPE / PHILOX: one N-wide vector per thread ---------------------------
-template <int N, int kRng, bool kFirst, bool kNext, bool kMerge = false>
-__global__ void __launch_bounds__(kBlock) substep_kernel(const SubstepArgs a) {
-  const uint32_t v = blockIdx.x * kBlock + threadIdx.x;
-  const uint32_t i = v * N;
-  if (i >= a.g.total) return;
+// ---- the memory side of a fused launch: one N-wide vector per thread ------------
+template <int N, bool kFirst, bool kNext, bool kMerge>
+__device__ __forceinline__ void substep_vector(const SubstepArgs& a, uint32_t i, const float (&xi1)[N],
+                                               const float (&xi2)[N]) {
   uint32_t row, mi;
   locate(a.g, i, row, mi);
-
-  float x[N], x0[N], x0b[N], y[N], cp[N], cn[N], te[N], xi1[N], xi2[N];
+  float x[N], x0[N], x0b[N], y[N], cp[N], cn[N], te[N];
   bool known[N];
   load_f<N>(a.x, i, x);
   load_f_ro<N>(a.x0, i, x0);
@@ -296,7 +293,25 @@ __global__ void __launch_bounds__(kBlock) substep_kernel(const SubstepArgs a) {
 #pragma unroll
     for (int j = 0; j < N; ++j) cp[j] = 0.f;
   }
+  RowCoef<kFirst, kNext> t;
+  t.load(a.table + (size_t)row * LP_TABLE_STRIDE);
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+    substep_element<kFirst, kNext, kMerge>(x[j], x0[j], x0b[j], y[j], cp[j], known[j], xi1[j], xi2[j], t, cn[j],
+                                           te[j]);
+  store_f<N>(a.x, i, x);
+  if (kNext || a.store_c) store_f<N>(a.c, i, cn);
+  if (a.x_copy) store_f<N>(a.x_copy, i, x);
+  if (a.x0e) store_f<N>(a.x0e, i, te);
+}
 
+// ---- TAPE / PHILOX ------------------------------------------------------------
+template <int N, int kRng, bool kFirst, bool kNext, bool kMerge = false>
+__global__ void __launch_bounds__(kBlock) substep_kernel(const SubstepArgs a) {
+  const uint32_t v = blockIdx.x * kBlock + threadIdx.x;
+  const uint32_t i = v * N;
+  if (i >= a.g.total) return;
+  float xi1[N], xi2[N];
   if (kRng == LP_RNG_TAPE) {
     load_f_ro<N>(a.tape0, i, xi1);
     if (kNext) {
@@ -323,21 +338,53 @@ __global__ void __launch_bounds__(kBlock) substep_kernel(const SubstepArgs a) {
       xi2[0] = pick(n2, i & 3);
     }
   }
-
-  RowCoef<kFirst, kNext> t;
-  t.load(a.table + (size_t)row * LP_TABLE_STRIDE);
-#pragma unroll
-  for (int j = 0; j < N; ++j)
-    substep_element<kFirst, kNext, kMerge>(x[j], x0[j], x0b[j], y[j], cp[j], known[j], xi1[j], xi2[j], t, cn[j],
-                                           te[j]);
-
-  store_f<N>(a.x, i, x);
-  if (kNext || a.store_c) store_f<N>(a.c, i, cn);
-  if (a.x_copy) store_f<N>(a.x_copy, i, x);
-  if (a.x0e) store_f<N>(a.x0e, i, te);
+  substep_vector<N, kFirst, kNext, kMerge>(a, i, xi1, xi2);
 }
 
-// ---- TORCH: torch.randn_like's own thread<->element mapping -----------------
+// ---- TORCH, 128-bit path --------------------------------------------------------
+// torch.randn_like gives element li the component ((li div T) mod 4) of the ((li div 4T))-th
+// curand_normal4 of Philox subsequence (li mod T).  Thread (t, k) of this kernel IS torch's thread t at
+// its k-th call: it generates that call's four normals (planes 4k..4k+3), then the four lanes of a quad
+// transpose them with shuffles so that lane q ends up with plane 4k+q of torch threads t0..t0+3 -- four
+// CONSECUTIVE elements, i.e. one float4 -- and runs the same vector body as the other modes.
+// One Philox call per 4 elements per draw, 128-bit accesses, bit-identical stream.
+__device__ __forceinline__ void quad_transpose(const float4& mine, uint32_t q, uint32_t lane, float (&out)[4]) {
+#pragma unroll
+  for (uint32_t r = 0; r < 4; ++r) {
+    const uint32_t src = (q + r) & 3u;                 // quad lane read in this round
+    const float give = pick(mine, (q - r) & 3u);       // what MY reader of this round needs from me
+    out[src] = __shfl_sync(0xffffffffu, give, (lane & ~3u) | src);
+  }
+}
+
+template <bool kFirst, bool kNext>
+__global__ void __launch_bounds__(kBlock) substep_torchvec_kernel(const SubstepArgs a) {
+  const uint32_t T = a.torch_T;
+  const uint32_t t = blockIdx.x * kBlock + threadIdx.x;  // torch thread == Philox subsequence (grid.x*256 == T)
+  const uint32_t k = blockIdx.y;                          // index of the curand_normal4 call
+  const uint32_t q = t & 3u;
+  uint64_t seed = a.seed, o0 = a.draw0, o1 = a.draw1;
+  if (a.rng_state) {
+    seed = a.rng_state[0];
+    o0 += a.rng_state[1];
+    o1 += a.rng_state[1];
+  }
+  const float4 n1 = torch_normal4(seed, o0, t, k);
+  float4 n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kNext) n2 = torch_normal4(seed, o1, t, k);
+  float xi1[4], xi2[4];
+  quad_transpose(n1, q, threadIdx.x & 31u, xi1);
+  if (kNext) {
+    quad_transpose(n2, q, threadIdx.x & 31u, xi2);
+  } else {
+    xi2[0] = xi2[1] = xi2[2] = xi2[3] = 0.f;
+  }
+  const uint64_t e = (uint64_t)(t - q) + (uint64_t)(4u * k + q) * T;  // first of my 4 consecutive elements
+  if (e >= a.g.total) return;
+  substep_vector<4, kFirst, kNext, false>(a, (uint32_t)e, xi1, xi2);
+}
+
+// ---- TORCH, scalar fallback: torch.randn_like's own thread<->element mapping ---
 // thread t of T handles elements t, t+T, t+2T, t+3T (one curand_normal4) per
 // 4T-stride iteration, exactly like distribution_elementwise_grid_stride_kernel
 // (ATen/native/cuda/DistributionTemplates.h), so one Philox call feeds 4
@@ -564,6 +611,30 @@ __global__ void __launch_bounds__(kBlock) epilogue_kernel(const float* __restric
   store_f<N>(out, i, ov);
 }
 
+template <int N>
+__global__ void __launch_bounds__(kBlock) epilogue_euler_kernel(const float* __restrict__ model_out,
+                                                                const float* __restrict__ y,
+                                                                const uint8_t* __restrict__ mask, float* x,
+                                                                float* out, float coef, Geometry g) {
+  const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
+  if (i >= g.total) return;
+  uint32_t row, mi;
+  locate(g, i, row, mi);
+  float ov[N], yv[N], xv[N];
+  bool known[N];
+  load_f_ro<N>(model_out, i, ov);
+  load_f_ro<N>(y, i, yv);
+  load_f<N>(x, i, xv);
+  load_m<N>(mask, mi, known);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    ov[j] = known[j] ? yv[j] : ov[j];
+    xv[j] = fmaf(xv[j] - ov[j], coef, xv[j]);
+  }
+  store_f<N>(out, i, ov);
+  store_f<N>(x, i, xv);
+}
+
 __global__ void __launch_bounds__(kBlock) pack_mask_kernel(const float* __restrict__ m, uint8_t* out,
                                                            uint32_t n, int invert) {
   const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
@@ -785,6 +856,18 @@ extern "C" int lp_substep_f32(float* x_model, const float* x0, const float* x0_b
     if (int rc = torch_grid(a.g.total, -1, &grid, nullptr)) return rc;
     a.torch_T = (uint32_t)(grid * 256);
     const unsigned gb = (unsigned)grid;
+    const bool tv4 = geometry_vec4(a.g, mask) && aligned16(x_model) && aligned16(x0) && aligned16(x0_big) &&
+                     aligned16(y) && (!c_state || aligned16(c_state)) && (!x_copy || aligned16(x_copy)) &&
+                     (!x0e_out || aligned16(x0e_out));
+    const uint64_t calls = ((uint64_t)a.g.total + 4ull * a.torch_T - 1) / (4ull * a.torch_T);
+    if (tv4 && calls <= 65535) {
+      const dim3 g2(gb, (unsigned)calls);
+      if (f && n) substep_torchvec_kernel<true, true><<<g2, kBlock, 0, s>>>(a);
+      else if (f) substep_torchvec_kernel<true, false><<<g2, kBlock, 0, s>>>(a);
+      else if (n) substep_torchvec_kernel<false, true><<<g2, kBlock, 0, s>>>(a);
+      else substep_torchvec_kernel<false, false><<<g2, kBlock, 0, s>>>(a);
+      return check_launch();
+    }
     if (f && n) substep_torch_kernel<true, true><<<gb, kBlock, 0, s>>>(a);
     else if (f) substep_torch_kernel<true, false><<<gb, kBlock, 0, s>>>(a);
     else if (n) substep_torch_kernel<false, true><<<gb, kBlock, 0, s>>>(a);
@@ -842,6 +925,19 @@ extern "C" int lp_epilogue_f32(const float* model_out, const float* y, const uin
   const bool v4 = geometry_vec4(g, mask) && aligned16(model_out) && aligned16(y) && aligned16(out);
   if (v4) epilogue_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(model_out, y, mask, out, g);
   else epilogue_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(model_out, y, mask, out, g);
+  return check_launch();
+}
+
+extern "C" int lp_epilogue_euler_f32(const float* model_out, const float* y, const uint8_t* mask, float* x_inout,
+                                     float* out, float euler_coef, const lp_dims* dims, lp_stream_t stream) {
+  if (!model_out || !y || !mask || !x_inout || !out) return LP_ERR_INVALID;
+  Geometry g;
+  if (int rc = make_geometry(dims, g)) return rc;
+  if (g.total == 0) return LP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool v4 = geometry_vec4(g, mask) && aligned16(model_out) && aligned16(y) && aligned16(out) && aligned16(x_inout);
+  if (v4) epilogue_euler_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(model_out, y, mask, x_inout, out, euler_coef, g);
+  else epilogue_euler_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(model_out, y, mask, x_inout, out, euler_coef, g);
   return check_launch();
 }
 

@@ -366,7 +366,7 @@ class LanPaint:
 
     # ---- the launch sequence of one outer step (shared by the eager path and graph capture) ----
     def _launch_sequence(self, xm, y, nz, pm, dims, tab, t_model, sigma_dev, cbuf, out, active, plan, call_scaling,
-                         model_options, seed, stopper, rng_state):
+                         model_options, seed, stopper, rng_state, euler_coef=None):
         lib = _native.load()
         dev = xm.device
         stream = _P(_stream_ptr(dev))
@@ -449,8 +449,13 @@ class LanPaint:
         self.model_calls += 1
         mo, _ = self.unpack_model_output(out_heads)
         mo = _as_operand(mo, xm)
-        rc = lib.lp_epilogue_f32(_P(mo.data_ptr()), _P(y.data_ptr()), _P(pm.data.data_ptr()), _P(out.data_ptr()),
-                                 C.byref(dims), stream)
+        if euler_coef is None:
+            rc = lib.lp_epilogue_f32(_P(mo.data_ptr()), _P(y.data_ptr()), _P(pm.data.data_ptr()), _P(out.data_ptr()),
+                                     C.byref(dims), stream)
+        else:  # host-owned sampler loop: fold k-diffusion's Euler update of x into the same pass
+            rc = lib.lp_epilogue_euler_f32(_P(mo.data_ptr()), _P(y.data_ptr()), _P(pm.data.data_ptr()),
+                                           _P(xm.data_ptr()), _P(out.data_ptr()), C.c_float(euler_coef),
+                                           C.byref(dims), stream)
         _native.check(rc, "lp_epilogue_f32")
         self.launches += 1
         return done

@@ -202,9 +202,10 @@ class GraphedJob:
 
     Semantics are exactly `euler_inpaint(engine, ...)` (asserted bit-for-bit by the tests)."""
 
-    def __init__(self, engine, sched: HostSchedule, shape, device, flow: bool = False):
+    def __init__(self, engine, sched: HostSchedule, shape, device, flow: bool = False, fused_euler: bool = True):
         import numpy as np
         from .engine import _DrawPlan
+        self.fused_euler = fused_euler   # Euler update inside lp_epilogue_euler_f32 instead of two torch kernels
         from .schedule import Hyper, build_table, mean_half_dt
         if engine.rng not in ("philox", "torch"):
             raise ValueError("GraphedJob needs an in-kernel RNG mode ('philox' or 'torch')")
@@ -245,9 +246,12 @@ class GraphedJob:
         self.x.copy_(sampling.noise_scaling(self.sigma0, self.noise, self.y))
         state = self.rng_state.data_ptr()
         for i, st in enumerate(self.sched.steps):
+            coef = (st.sigma_next - st.sigma) / st.sigma
             eng._launch_sequence(self.x, self.y, self.noise, pm, dims, self.tables[i], self.t_model[i], self.sigma[i],
-                                 self.c, self.out, self.active[i], plan, False, None, 0, None, state)
-            self.x.add_(self.x - self.out, alpha=(st.sigma_next - st.sigma) / st.sigma)
+                                 self.c, self.out, self.active[i], plan, False, None, 0, None, state,
+                                 euler_coef=coef if self.fused_euler else None)
+            if not self.fused_euler:
+                self.x.add_(self.x - self.out, alpha=coef)
 
     def _capture(self, pm):
         import numpy as np

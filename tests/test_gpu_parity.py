@@ -493,10 +493,13 @@ def test_whole_job_graph_equals_step_by_step(rng, cuda_device):
     off1 = torch.cuda.default_generators[dev.index].get_offset()
     torch.manual_seed(4)
     e2 = engine()
-    job = GraphedJob(e2, sched, shape, dev)
+    job = GraphedJob(e2, sched, shape, dev, fused_euler=False)
     got = job.run(y, noise, m)
     off2 = torch.cuda.default_generators[dev.index].get_offset()
     assert torch.equal(got, want) and off1 == off2
+    torch.manual_seed(4)
+    fused = GraphedJob(engine(), sched, shape, dev, fused_euler=True).run(y, noise, m)   # Euler inside the epilogue
+    assert max_rel(fused, want) <= 1e-5
     assert e2.model_calls == e1.model_calls == 73 and e2.substeps_done == 53
     again = job.run(y, noise, m)          # a second request batch: fresh noise, same graph
     assert not torch.equal(again, got) and torch.isfinite(again).all()
