@@ -348,13 +348,22 @@ __global__ void __launch_bounds__(kBlock) substep_kernel(const SubstepArgs a) {
 // transpose them with shuffles so that lane q ends up with plane 4k+q of torch threads t0..t0+3 -- four
 // CONSECUTIVE elements, i.e. one float4 -- and runs the same vector body as the other modes.
 // One Philox call per 4 elements per draw, 128-bit accesses, bit-identical stream.
-__device__ __forceinline__ void quad_transpose(const float4& mine, uint32_t q, uint32_t lane, float (&out)[4]) {
-#pragma unroll
-  for (uint32_t r = 0; r < 4; ++r) {
-    const uint32_t src = (q + r) & 3u;                 // quad lane read in this round
-    const float give = pick(mine, (q - r) & 3u);       // what MY reader of this round needs from me
-    out[src] = __shfl_sync(0xffffffffu, give, (lane & ~3u) | src);
-  }
+// 4x4 transpose across the 4 lanes of a quad, two butterfly stages, register indices all static:
+// in: v[j] = my normal for plane j;  out: v[i] = plane q's normal of quad lane i.
+__device__ __forceinline__ void quad_transpose(float (&v)[4], uint32_t q) {
+  const bool b0 = (q & 1u) != 0, b1 = (q & 2u) != 0;
+  // stage 1: 2x2 blocks between lanes q and q^1
+  float s0 = b0 ? v[0] : v[1], s1 = b0 ? v[2] : v[3];
+  s0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+  s1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+  v[0] = b0 ? s0 : v[0]; v[1] = b0 ? v[1] : s0;
+  v[2] = b0 ? s1 : v[2]; v[3] = b0 ? v[3] : s1;
+  // stage 2: 2x2 blocks of pairs between lanes q and q^2
+  float u0 = b1 ? v[0] : v[2], u1 = b1 ? v[1] : v[3];
+  u0 = __shfl_xor_sync(0xffffffffu, u0, 2);
+  u1 = __shfl_xor_sync(0xffffffffu, u1, 2);
+  v[0] = b1 ? u0 : v[0]; v[2] = b1 ? v[2] : u0;
+  v[1] = b1 ? u1 : v[1]; v[3] = b1 ? v[3] : u1;
 }
 
 template <bool kFirst, bool kNext>
@@ -372,13 +381,10 @@ __global__ void __launch_bounds__(kBlock) substep_torchvec_kernel(const SubstepA
   const float4 n1 = torch_normal4(seed, o0, t, k);
   float4 n2 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (kNext) n2 = torch_normal4(seed, o1, t, k);
-  float xi1[4], xi2[4];
-  quad_transpose(n1, q, threadIdx.x & 31u, xi1);
-  if (kNext) {
-    quad_transpose(n2, q, threadIdx.x & 31u, xi2);
-  } else {
-    xi2[0] = xi2[1] = xi2[2] = xi2[3] = 0.f;
-  }
+  float xi1[4] = {n1.x, n1.y, n1.z, n1.w};
+  float xi2[4] = {n2.x, n2.y, n2.z, n2.w};
+  quad_transpose(xi1, q);
+  if (kNext) quad_transpose(xi2, q);
   const uint64_t e = (uint64_t)(t - q) + (uint64_t)(4u * k + q) * T;  // first of my 4 consecutive elements
   if (e >= a.g.total) return;
   substep_vector<4, kFirst, kNext, false>(a, (uint32_t)e, xi1, xi2);
