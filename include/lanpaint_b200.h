@@ -168,6 +168,18 @@ int lp_substep_f32(float* x_model, const float* x0, const float* x0_big, const f
                    const float* table, const lp_dims* dims, const lp_rng* rng, int flags,
                    lp_stream_t stream);
 
+/* lp_substep_f32 with the two classifier-free-guidance combines folded in (replaces the
+ * two cfg_function calls of sampling_function_LanPaint, src/LanPaint/nodes.py:175): the caller passes the
+ * network's raw cond / uncond x0 predictions and the two scales,
+ *   x0 = uncond + (cond - uncond) * cfg ;   x0_big = uncond + (cond - uncond) * cfg_big
+ * evaluated with the same three roundings as the eager sub/mul/add, so results equal the unfused path bit
+ * for bit.  Same bytes read as lp_substep_f32; saves the 2 x 3 element-wise kernels and 2 tensors of
+ * traffic the combines cost per model call. */
+int lp_substep_cfg_f32(float* x_model, const float* cond, const float* uncond, float cfg, float cfg_big,
+                       const float* y, const uint8_t* mask, float* c_state, float* x_copy, float* x0e_out,
+                       const float* table, const lp_dims* dims, const lp_rng* rng, int flags,
+                       lp_stream_t stream);
+
 /* The un-fused building block: one exact OU advance of the model-space state,
  *   x_t = x/S;  x_t = e x_t + k C + sd xi;  x = x_t S
  * over dt (half = 0) or dt/2 (half = 1) -- advance_time_overdamped,
@@ -186,6 +198,11 @@ int lp_epilogue_f32(const float* model_out, const float* y, const uint8_t* mask,
  * x_inout is the model-space state lp_substep_f32 left behind (the rewritten sampler x). */
 int lp_epilogue_euler_f32(const float* model_out, const float* y, const uint8_t* mask, float* x_inout,
                           float* out, float euler_coef, const lp_dims* dims, lp_stream_t stream);
+
+/* Final denoise of an outer step straight from raw cond / uncond predictions:
+ *   out = mask ? y : uncond + (cond - uncond)*cfg ;  if x_inout != NULL: x = x + (x - out)*euler_coef. */
+int lp_epilogue_cfg_f32(const float* cond, const float* uncond, float cfg, const float* y, const uint8_t* mask,
+                        float* x_inout, float* out, float euler_coef, const lp_dims* dims, lp_stream_t stream);
 
 /* Early-stop statistics (LanPaintEarlyStopper, src/LanPaint/earlystop.py:32-55,238-313):
  *   sums[0] = sum over elements with mask == 0 (the inpaint weight)  of (scale*(a-b))^2

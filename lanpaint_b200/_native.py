@@ -21,8 +21,8 @@ SUBSTEP_FIRST, SUBSTEP_FUSE_NEXT, SUBSTEP_STORE_C, SUBSTEP_MERGE_NOISE = 1, 2, 4
 # every symbol include/lanpaint_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = (
     "lp_abi_version", "lp_status_string", "lp_last_cuda_error", "lp_build_coef_table",
-    "lp_torch_randn_geometry", "lp_pack_mask_f32", "lp_prologue_f32", "lp_substep_f32", "lp_advance_f32",
-    "lp_epilogue_f32", "lp_epilogue_euler_f32", "lp_stop_stats_f32", "lp_fill_normal_f32", "lp_synth_denoiser_f32", "lp_l2_flush",
+    "lp_torch_randn_geometry", "lp_pack_mask_f32", "lp_prologue_f32", "lp_substep_f32", "lp_substep_cfg_f32", "lp_advance_f32",
+    "lp_epilogue_f32", "lp_epilogue_euler_f32", "lp_epilogue_cfg_f32", "lp_stop_stats_f32", "lp_fill_normal_f32", "lp_synth_denoiser_f32", "lp_l2_flush",
 )
 
 
@@ -79,6 +79,11 @@ def load() -> C.CDLL:
     lib.lp_prologue_f32.argtypes = [p, p, p, p, p, p, p, C.POINTER(Dims), p]
     lib.lp_substep_f32.restype = i32
     lib.lp_substep_f32.argtypes = [p, p, p, p, p, p, p, p, p, C.POINTER(Dims), C.POINTER(Rng), i32, p]
+    lib.lp_substep_cfg_f32.restype = i32
+    lib.lp_substep_cfg_f32.argtypes = [p, p, p, C.c_float, C.c_float, p, p, p, p, p, p, C.POINTER(Dims), C.POINTER(Rng),
+                                       i32, p]
+    lib.lp_epilogue_cfg_f32.restype = i32
+    lib.lp_epilogue_cfg_f32.argtypes = [p, p, C.c_float, p, p, p, p, C.c_float, C.POINTER(Dims), p]
     lib.lp_advance_f32.restype = i32
     lib.lp_advance_f32.argtypes = [p, p, p, p, C.POINTER(Dims), C.POINTER(Rng), i32, p]
     lib.lp_epilogue_f32.restype = i32

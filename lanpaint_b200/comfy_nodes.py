@@ -38,7 +38,7 @@ try:  # WAN22 exists only in recent ComfyUI builds
 except Exception:  # pragma: no cover
     WAN22 = None
 
-from .engine import LanPaint, pack_mask
+from .engine import CfgPair, LanPaint, pack_mask
 from .schedule import effective_inner_steps, min_step_frac_effective_steps, times_from_sigma  # noqa: F401
 
 FLOW_MODEL_TYPES = (ModelType.FLOW, getattr(ModelType, "FLOW_AV", None))
@@ -167,6 +167,12 @@ def sampling_function_LanPaint(model, x, timestep, uncond, cond, cond_scale, con
     for fn in model_options.get("sampler_pre_cfg_function", []):
         out = fn({"conds": conds, "conds_out": out, "cond_scale": cond_scale, "timestep": timestep, "input": x,
                   "sigma": timestep, "model": model, "model_options": model_options})
+    opts = model_options.get("lanpaint_b200", {}) if isinstance(model_options, dict) else {}
+    plain_cfg = ("sampler_cfg_function" not in model_options and not model_options.get("sampler_post_cfg_function")
+                 and uncond_ is not None and isinstance(out[0], torch.Tensor) and isinstance(out[1], torch.Tensor))
+    if plain_cfg and opts.get("fused_cfg", True):
+        # nothing needs the combined tensors materialised: hand cond/uncond to the fused kernel
+        return CfgPair(out[0], out[1], cond_scale, cond_scale_BIG)
     combine = comfy.samplers.cfg_function
     return (combine(model, out[0], out[1], cond_scale, x, timestep, model_options=model_options, cond=cond, uncond=uncond_),
             combine(model, out[0], out[1], cond_scale_BIG, x, timestep, model_options=model_options, cond=cond, uncond=uncond_))

@@ -215,6 +215,8 @@ struct SubstepArgs {
   Geometry g;
   uint32_t torch_T;  // threads of torch's randn grid (LP_RNG_TORCH)
   int store_c;       // write C even when the next half-advance is not fused
+  int use_cfg;       // x0/x0b hold raw cond/uncond predictions: combine them here
+  float cfg, cfg_big;
 };
 
 template <int N>
@@ -284,6 +286,14 @@ __device__ __forceinline__ void substep_vector(const SubstepArgs& a, uint32_t i,
   } else {
 #pragma unroll
     for (int j = 0; j < N; ++j) x0b[j] = x0[j];
+  }
+  if (a.use_cfg) {  // x0 = cond, x0b = uncond: u + (c-u)*s with the eager path's three roundings
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const float u = x0b[j], d = __fsub_rn(x0[j], u);
+      x0[j] = __fadd_rn(u, __fmul_rn(d, a.cfg));
+      x0b[j] = __fadd_rn(u, __fmul_rn(d, a.cfg_big));
+    }
   }
   load_f_ro<N>(a.y, i, y);
   load_m<N>(a.mask, mi, known);
@@ -421,8 +431,13 @@ __global__ void __launch_bounds__(kBlock) substep_torch_kernel(const SubstepArgs
       RowCoef<kFirst, kNext> t;
       t.load(a.table + (size_t)row * LP_TABLE_STRIDE);
       float x = a.x[i];
-      const float x0 = __ldg(a.x0 + i);
-      const float x0b = __ldg(a.x0b + i);
+      float x0 = __ldg(a.x0 + i);
+      float x0b = __ldg(a.x0b + i);
+      if (a.use_cfg) {
+        const float u = x0b, d = __fsub_rn(x0, u);
+        x0 = __fadd_rn(u, __fmul_rn(d, a.cfg));
+        x0b = __fadd_rn(u, __fmul_rn(d, a.cfg_big));
+      }
       const float y = __ldg(a.y + i);
       const bool known = __ldg(a.mask + mi) != 0;
       const float cp = kFirst ? 0.f : a.c[i];
@@ -641,6 +656,33 @@ __global__ void __launch_bounds__(kBlock) epilogue_euler_kernel(const float* __r
   store_f<N>(x, i, xv);
 }
 
+template <int N>
+__global__ void __launch_bounds__(kBlock) epilogue_cfg_kernel(const float* __restrict__ cond,
+                                                              const float* __restrict__ uncond, float cfg,
+                                                              const float* __restrict__ y,
+                                                              const uint8_t* __restrict__ mask, float* x, float* out,
+                                                              float coef, Geometry g) {
+  const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
+  if (i >= g.total) return;
+  uint32_t row, mi;
+  locate(g, i, row, mi);
+  float cv[N], uv[N], yv[N], xv[N];
+  bool known[N];
+  load_f_ro<N>(cond, i, cv);
+  load_f_ro<N>(uncond, i, uv);
+  load_f_ro<N>(y, i, yv);
+  load_m<N>(mask, mi, known);
+  if (x) load_f<N>(x, i, xv);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float o = __fadd_rn(uv[j], __fmul_rn(__fsub_rn(cv[j], uv[j]), cfg));
+    cv[j] = known[j] ? yv[j] : o;
+    if (x) xv[j] = fmaf(xv[j] - cv[j], coef, xv[j]);
+  }
+  store_f<N>(out, i, cv);
+  if (x) store_f<N>(x, i, xv);
+}
+
 __global__ void __launch_bounds__(kBlock) pack_mask_kernel(const float* __restrict__ m, uint8_t* out,
                                                            uint32_t n, int invert) {
   const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
@@ -833,10 +875,10 @@ extern "C" int lp_prologue_f32(const float* x, const float* y, const float* nois
   return check_launch();
 }
 
-extern "C" int lp_substep_f32(float* x_model, const float* x0, const float* x0_big, const float* y,
-                              const uint8_t* mask, float* c_state, float* x_copy, float* x0e_out,
-                              const float* table, const lp_dims* dims, const lp_rng* rng, int flags,
-                              lp_stream_t stream) {
+static int substep_impl(float* x_model, const float* x0, const float* x0_big, const float* y,
+                        const uint8_t* mask, float* c_state, float* x_copy, float* x0e_out, const float* table,
+                        const lp_dims* dims, const lp_rng* rng, int flags, lp_stream_t stream, int use_cfg,
+                        float cfg, float cfg_big) {
   if (!x_model || !x0 || !y || !mask || !table || !rng) return LP_ERR_INVALID;
   if (flags & ~(LP_SUBSTEP_FIRST | LP_SUBSTEP_FUSE_NEXT | LP_SUBSTEP_STORE_C | LP_SUBSTEP_MERGE_NOISE))
     return LP_ERR_INVALID;
@@ -854,6 +896,7 @@ extern "C" int lp_substep_f32(float* x_model, const float* x0, const float* x0_b
   a.tape0 = rng->tape0; a.tape1 = rng->tape1; a.rng_state = rng->state;
   a.seed = rng->seed; a.draw0 = rng->draw0; a.draw1 = rng->draw1; a.torch_T = 0;
   a.store_c = (flags & LP_SUBSTEP_STORE_C) != 0;
+  a.use_cfg = use_cfg; a.cfg = cfg; a.cfg_big = cfg_big;
   cudaStream_t s = (cudaStream_t)stream;
   const bool f = first != 0, n = has_next != 0;
 
@@ -894,6 +937,38 @@ extern "C" int lp_substep_f32(float* x_model, const float* x0, const float* x0_b
               : launch_substep_vec<1, LP_RNG_PHILOX>(a, f, n, merge, s);
   }
   return LP_ERR_INVALID;
+}
+
+extern "C" int lp_substep_f32(float* x_model, const float* x0, const float* x0_big, const float* y,
+                              const uint8_t* mask, float* c_state, float* x_copy, float* x0e_out,
+                              const float* table, const lp_dims* dims, const lp_rng* rng, int flags,
+                              lp_stream_t stream) {
+  return substep_impl(x_model, x0, x0_big, y, mask, c_state, x_copy, x0e_out, table, dims, rng, flags, stream, 0,
+                      0.f, 0.f);
+}
+
+extern "C" int lp_substep_cfg_f32(float* x_model, const float* cond, const float* uncond, float cfg, float cfg_big,
+                                  const float* y, const uint8_t* mask, float* c_state, float* x_copy,
+                                  float* x0e_out, const float* table, const lp_dims* dims, const lp_rng* rng,
+                                  int flags, lp_stream_t stream) {
+  if (!uncond || uncond == cond) return LP_ERR_INVALID;
+  return substep_impl(x_model, cond, uncond, y, mask, c_state, x_copy, x0e_out, table, dims, rng, flags, stream, 1,
+                      cfg, cfg_big);
+}
+
+extern "C" int lp_epilogue_cfg_f32(const float* cond, const float* uncond, float cfg, const float* y,
+                                   const uint8_t* mask, float* x_inout, float* out, float euler_coef,
+                                   const lp_dims* dims, lp_stream_t stream) {
+  if (!cond || !uncond || !y || !mask || !out) return LP_ERR_INVALID;
+  Geometry g;
+  if (int rc = make_geometry(dims, g)) return rc;
+  if (g.total == 0) return LP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool v4 = geometry_vec4(g, mask) && aligned16(cond) && aligned16(uncond) && aligned16(y) && aligned16(out) &&
+                  (!x_inout || aligned16(x_inout));
+  if (v4) epilogue_cfg_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(cond, uncond, cfg, y, mask, x_inout, out, euler_coef, g);
+  else epilogue_cfg_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(cond, uncond, cfg, y, mask, x_inout, out, euler_coef, g);
+  return check_launch();
 }
 
 extern "C" int lp_advance_f32(float* x_model, const float* c_state, const uint8_t* mask, const float* table,

@@ -69,6 +69,24 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
+class CfgPair:
+    """Raw network outputs of one cond/uncond evaluation plus the two guidance scales.
+
+    The patched guider returns this instead of the two combined tensors when no user hook needs
+    them materialised (comfy_nodes.sampling_function_LanPaint); the engine then feeds cond/uncond
+    straight to `lp_substep_cfg_f32`, which does both `uncond + (cond - uncond)*scale` combines in
+    registers.  `heads()` gives the eager equivalent for any other consumer."""
+
+    __slots__ = ("cond", "uncond", "cfg", "cfg_big")
+
+    def __init__(self, cond: torch.Tensor, uncond: torch.Tensor, cfg: float, cfg_big: float):
+        self.cond, self.uncond, self.cfg, self.cfg_big = cond, uncond, float(cfg), float(cfg_big)
+
+    def heads(self):
+        d = self.cond - self.uncond
+        return self.uncond + d * self.cfg, self.uncond + d * self.cfg_big
+
+
 class PackedMask:
     """uint8 known-region mask + the strides the kernels index it with."""
 
@@ -197,6 +215,8 @@ class LanPaint:
         return array[(slice(None),) + (0,) * (self.img_dim_size - 1)]
 
     def unpack_model_output(self, output):
+        if isinstance(output, CfgPair):
+            return output.heads()
         if isinstance(output, (tuple, list)):
             if len(output) >= 2:
                 return output[0], output[1]
@@ -386,11 +406,16 @@ class LanPaint:
             first = i == 0
             has_next = i + 1 < active
             self.model_calls += 1
+            pair = None
             if stopper is None or first:
                 heads = self.inner_model(xm, t_model, model_options=model_options, seed=seed)
-                h0, h1 = self.unpack_model_output(heads)
-                x0 = _as_operand(h0, xm)
-                x0b = x0 if h1 is h0 else _as_operand(h1, xm)
+                if isinstance(heads, CfgPair) and stopper is None:
+                    pair = heads
+                    x0, x0b = _as_operand(pair.cond, xm), _as_operand(pair.uncond, xm)
+                else:
+                    h0, h1 = self.unpack_model_output(heads)
+                    x0 = _as_operand(h0, xm)
+                    x0b = x0 if h1 is h0 else _as_operand(h1, xm)
             if stopper is None:
                 # fused: post-model half of sub-step i + pre-model half of sub-step i+1
                 flags = (F.SUBSTEP_FIRST if first else 0) | (F.SUBSTEP_FUSE_NEXT if has_next else 0)
@@ -399,9 +424,15 @@ class LanPaint:
                     flags |= F.SUBSTEP_MERGE_NOISE
                 r = plan.rng_struct(2 if (has_next and not merge) else 1, rng_state)
                 ev = self._event_pair(flags) if self.kernel_timer is not None else None
-                rc = lib.lp_substep_f32(_P(xm.data_ptr()), _P(x0.data_ptr()), _P(x0b.data_ptr()),
-                                        _P(y.data_ptr()), _P(pm.data.data_ptr()), _P(cbuf.data_ptr()), None, None,
-                                        _P(tab.data_ptr()), C.byref(dims), C.byref(r), flags, stream)
+                if pair is None:
+                    rc = lib.lp_substep_f32(_P(xm.data_ptr()), _P(x0.data_ptr()), _P(x0b.data_ptr()),
+                                            _P(y.data_ptr()), _P(pm.data.data_ptr()), _P(cbuf.data_ptr()), None,
+                                            None, _P(tab.data_ptr()), C.byref(dims), C.byref(r), flags, stream)
+                else:  # both CFG combines happen inside the kernel
+                    rc = lib.lp_substep_cfg_f32(_P(xm.data_ptr()), _P(x0.data_ptr()), _P(x0b.data_ptr()),
+                                                C.c_float(pair.cfg), C.c_float(pair.cfg_big), _P(y.data_ptr()),
+                                                _P(pm.data.data_ptr()), _P(cbuf.data_ptr()), None, None,
+                                                _P(tab.data_ptr()), C.byref(dims), C.byref(r), flags, stream)
                 if ev is not None:
                     ev[1].record()
                 _native.check(rc, "lp_substep_f32")
@@ -447,6 +478,15 @@ class LanPaint:
         # final denoise + known-region paste (lanpaint.py:151-157)
         out_heads = self.inner_model(xm, sigma_dev, model_options=model_options, seed=seed)
         self.model_calls += 1
+        if isinstance(out_heads, CfgPair):
+            cd, uc = _as_operand(out_heads.cond, xm), _as_operand(out_heads.uncond, xm)
+            rc = lib.lp_epilogue_cfg_f32(_P(cd.data_ptr()), _P(uc.data_ptr()), C.c_float(out_heads.cfg),
+                                         _P(y.data_ptr()), _P(pm.data.data_ptr()),
+                                         _P(xm.data_ptr()) if euler_coef is not None else None, _P(out.data_ptr()),
+                                         C.c_float(euler_coef or 0.0), C.byref(dims), stream)
+            _native.check(rc, "lp_epilogue_cfg_f32")
+            self.launches += 1
+            return done
         mo, _ = self.unpack_model_output(out_heads)
         mo = _as_operand(mo, xm)
         if euler_coef is None:

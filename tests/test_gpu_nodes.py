@@ -106,3 +106,41 @@ def test_heun_sampler_calls_wrapper_twice_per_step(cuda_device):
                                                   2, 5.0, 0.2, "Image First", "", N.IMAGE_MODE)
     assert torch.isfinite(out["samples"]).all()
     assert N.LAST_ENGINE["engine"].model_calls > 6
+
+
+def test_fused_cfg_equals_materialised_combines(cuda_device):
+    """cond/uncond fed straight to lp_substep_cfg_f32 == the two eager cfg_function
+    combines of nodes.py:175, bit for bit (same three roundings), and fewer launches."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    dev = cuda_device
+    g = torch.Generator().manual_seed(0)
+    y = torch.randn(2, 4, 32, 32, generator=g)
+    noise_mask = (torch.rand(2, 1, 32, 32, generator=g) < 0.5).float()
+    res = {}
+    for fused in (True, False):
+        patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+        patcher.model_options["lanpaint_b200"] = {"fused_cfg": fused}
+        (out,) = N.LanPaint_KSampler().sample(patcher, 7, 12, 6.5, "euler", "karras", 0.3, -0.2,
+                                              {"samples": y, "noise_mask": noise_mask}, 1.0, 4, "Prompt First", "",
+                                              N.IMAGE_MODE)
+        res[fused] = out["samples"]
+    assert torch.equal(res[True], res[False])
+
+
+def test_post_cfg_hook_disables_the_fusion(cuda_device):
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    from lanpaint_b200.engine import CfgPair
+    dev = cuda_device
+    x = torch.randn(1, 4, 8, 8, device=dev)
+    model = minicomfy.BaseModel(_denoiser)
+    t = torch.ones(1, device=dev)
+    plain = N.sampling_function_LanPaint(model, x, t, -0.2, 0.3, 5.0, 2.0, model_options={})
+    assert isinstance(plain, CfgPair)
+    h0, h1 = plain.heads()
+    hooked = N.sampling_function_LanPaint(model, x, t, -0.2, 0.3, 5.0, 2.0,
+                                          model_options={"sampler_post_cfg_function": [lambda a: a["denoised"]]})
+    assert isinstance(hooked, tuple) and torch.equal(hooked[0], h0) and torch.equal(hooked[1], h1)
+    cfg1 = N.sampling_function_LanPaint(model, x, t, -0.2, 0.3, 1.0, 1.0, model_options={})
+    assert isinstance(cfg1, tuple)   # uncond skipped at cfg == 1: nothing to fuse
