@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 2
+#define LP_ABI_VERSION 3
 #define LP_TABLE_STRIDE 32 /* floats per table row (one 128-byte line), layout below */
 
 typedef void* lp_stream_t; /* a cudaStream_t / CUstream */
@@ -84,6 +84,10 @@ typedef struct lp_dims {
   int64_t spatial;             /* elements per channel */
   int64_t mask_row_stride;     /* mask elements between consecutive rows */
   int64_t mask_channel_stride; /* 0 = mask broadcast over channels, spatial = full-shape mask */
+  int64_t row_split;           /* 0 = off.  > 0: positions >= row_split inside every row use table row
+                                  (n_rows + row) instead of (row): the MiniMax-H3 flat pack, whose trailing
+                                  audio positions run on their own sigma schedule (lanpaint.py:60-74); the
+                                  table then holds 2*n_rows rows */
 } lp_dims;
 
 /* How the Gaussian draws of src/LanPaint/lanpaint.py:252 (torch.randn_like on

@@ -11,7 +11,7 @@ from typing import Optional
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "liblanpaint_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 TABLE_STRIDE = 32
 
 RNG_TAPE, RNG_PHILOX, RNG_TORCH = 0, 1, 2
@@ -37,7 +37,7 @@ class Hyper(C.Structure):
 
 class Dims(C.Structure):
     _fields_ = [("n_rows", C.c_int64), ("per_row", C.c_int64), ("spatial", C.c_int64),
-                ("mask_row_stride", C.c_int64), ("mask_channel_stride", C.c_int64)]
+                ("mask_row_stride", C.c_int64), ("mask_channel_stride", C.c_int64), ("row_split", C.c_int64)]
 
 
 class Rng(C.Structure):

@@ -188,14 +188,18 @@ struct Geometry {
   uint32_t mask_channel_stride;
   FastDiv per_row;    // elements per table row
   FastDiv spatial;    // elements per channel
+  uint32_t n_rows;
+  uint32_t row_split; // 0 = off; positions >= row_split of a row use table row n_rows + row
 };
 
+// element index -> (table row, mask element)
 __device__ __forceinline__ void locate(const Geometry& g, uint32_t i, uint32_t& row, uint32_t& mask_index) {
   row = g.per_row.div(i);
   const uint32_t r = i - row * g.per_row.d;
   const uint32_t ch = g.spatial.div(r);
   const uint32_t s = r - ch * g.spatial.d;
   mask_index = row * g.mask_row_stride + ch * g.mask_channel_stride + s;
+  if (g.row_split && r >= g.row_split) row += g.n_rows;
 }
 
 struct SubstepArgs {
@@ -779,12 +783,15 @@ inline int make_geometry(const lp_dims* d, Geometry& g) {
   g.spatial = make_fastdiv(static_cast<uint32_t>(d->spatial));
   g.mask_row_stride = static_cast<uint32_t>(d->mask_row_stride);
   g.mask_channel_stride = static_cast<uint32_t>(d->mask_channel_stride);
+  if (d->row_split < 0 || d->row_split > d->per_row) return LP_ERR_INVALID;
+  g.n_rows = static_cast<uint32_t>(d->n_rows);
+  g.row_split = static_cast<uint32_t>(d->row_split);
   return LP_OK;
 }
 
 // 128-bit path needs every row / channel / mask offset to stay 4-aligned.
 inline bool geometry_vec4(const Geometry& g, const uint8_t* mask) {
-  return g.per_row.d % 4 == 0 && g.spatial.d % 4 == 0 && g.mask_row_stride % 4 == 0 &&
+  return g.per_row.d % 4 == 0 && g.spatial.d % 4 == 0 && g.row_split % 4 == 0 && g.mask_row_stride % 4 == 0 &&
          g.mask_channel_stride % 4 == 0 && aligned4(mask);
 }
 

@@ -201,6 +201,7 @@ class LanPaint:
         self.substeps_done = 0
         self._mask_cache = _IdentityCache()
         self._noise_zero_cache = _IdentityCache()
+        self._av_cache = _IdentityCache()
         self._ws = {}
         self.kernel_timer = None  # set to a list to collect (flags, start_event, stop_event) per substep launch
         _native.load()  # fail at construction, loudly, if the CUDA library is absent
@@ -619,8 +620,77 @@ class LanPaint:
                             packed_mask=pm, like=like, abt_mean=float(np.float32(abt_h.astype(np.float32).mean())),
                             dims=dims)
 
-    def _av_call(self, *a, **k):
-        raise NotImplementedError("MiniMax-H3 per-row audio schedule is not built yet (SURVEY 8f rank 4)")
+    # ---- MiniMax-H3 AV flat pack: trailing audio positions on their own schedule ----------------
+    def _av_split(self, ai: torch.Tensor, n_last: int) -> int:
+        """Validate that the indicator marks a suffix of the last axis and return where it starts
+        (nodes.py:346: audio_indicator[..., video_n:] = 1).  One read-back per distinct indicator."""
+        hit = self._av_cache.get(ai)
+        if hit is not None:
+            return hit
+        flat = ai.reshape(-1, ai.shape[-1])
+        if ai.shape[-1] != n_last or not bool((flat == flat[:1]).all()):
+            raise NotImplementedError("audio_indicator must mark the same positions of the last axis on every row")
+        line = (flat[0] > 0.5)
+        split = int((~line).sum().item())
+        if not bool(line[split:].all()) or bool(line[:split].any()):
+            raise NotImplementedError("audio_indicator must be a suffix of the last axis (a flat AV pack)")
+        self._av_cache.put(ai, split)
+        return split
+
+    def _av_call(self, x, sigma, latent_mask, current_times, n_steps, model_options, seed, flow, opts):
+        """lanpaint.py:60-74,173-180: audio positions take (VE, abt) and the replace sigma from the audio
+        schedule and pull the model's target back by `audio_correction`; everything else is unchanged.
+        Implemented with lp_dims.row_split: every row of the last axis has a second table row for its
+        audio suffix, so the launches are the same single fused kernels."""
+        rng = opts.get("rng", self.rng)
+        dev = x.device
+        if x.shape[0] != 1:
+            raise NotImplementedError("AV per-row schedule needs batch 1 (the reference's broadcasting does too)")
+        n_last = x.shape[-1]
+        lines = x.numel() // n_last
+        split = self._av_split(self.audio_indicator.to(dev), n_last)
+        VE_Sigma, abt, Flow_t = current_times
+        VE_a, abt_a, Flow_a = self.current_times_audio
+        corr_t = self.audio_correction
+        t_model_src = Flow_t if flow else VE_Sigma
+        scal = [sigma, VE_Sigma, abt, t_model_src, VE_a, abt_a, Flow_a]
+        vals = [t.reshape(-1)[:1].to(device=dev, dtype=torch.float32) for t in scal]
+        if corr_t is not None:
+            vals.append(corr_t.to(dev).reshape(-1)[-1:].float())   # an audio position (the last one)
+        host = torch.cat(vals).cpu().numpy().astype(np.float64)
+        s_v, ve_v, abt_v, tm_v, ve_au, abt_au, s_au = host[:7]
+        c_au = float(host[7]) if corr_t is not None else 1.0
+        hyper = Hyper(self.step_size, self.chara_lamb, self.chara_beta, self.min_step_frac, flow)
+        ns = float(getattr(self.inner_model.inner_model.model_sampling, "noise_scale", 1.0))
+        f32 = np.float32
+        rep_n = [float(f32(s_v) * f32(ns))] * lines + [float(f32(s_au) * f32(ns))] * lines   # lanpaint.py:91-92
+        rep_y = [float(f32(1.0) - f32(s_v))] * lines + [float(f32(1.0) - f32(s_au))] * lines
+        table_np = build_table([abt_v] * lines + [abt_au] * lines, [ve_v] * lines + [ve_au] * lines, hyper,
+                               rep_n, rep_y, [1.0] * lines + [c_au] * lines)
+
+        xm = x if (x.dtype == torch.float32 and x.is_contiguous()) else _f32c(x)
+        y = _f32c(self.latent_image.to(dev))
+        nz = _f32c(self.noise.to(dev))
+        pm = self._mask_cache.get(latent_mask) if isinstance(latent_mask, torch.Tensor) else None
+        if pm is None:
+            full = latent_mask.to(dev).expand(x.shape) if isinstance(latent_mask, torch.Tensor) else latent_mask
+            pm = pack_mask(full.reshape(1, 1, -1), xm.reshape(1, 1, -1))
+            self._mask_cache.put(latent_mask, pm)
+            self.launches += 1
+        dims = _native.Dims(lines, n_last, n_last, n_last, 0, split)
+        tab = torch.from_numpy(table_np).to(dev)
+        t_model = t_model_src.reshape(-1).to(dev)
+        active = n_steps if mean_half_dt([abt_v, abt_au], hyper) > 0.0 else 0
+        plan = _DrawPlan(rng, xm, active)
+        out = torch.empty_like(xm)
+        cbuf = torch.empty_like(xm)
+        done = self._launch_sequence(xm, y, nz, pm, dims, tab, t_model, sigma.to(dev), cbuf, out, active, plan, False,
+                                     model_options, seed, None, None)
+        plan.finish()
+        self.substeps_done += done
+        if xm is not x:
+            x.copy_(xm)
+        return out if out.dtype == x.dtype else out.to(x.dtype)
 
 
 def _repair_generator_after_failed_capture(dev: torch.device) -> None:

@@ -263,3 +263,58 @@ def dump_earlystop():
 
 if __name__ == "__main__" and "--earlystop" in sys.argv:
     dump_earlystop()
+
+
+# --------------------------------------------------------------------------------------------
+# MiniMax-H3 AV per-row schedule goldens (lanpaint.py:60-74,173-180): flat pack [1,C,N], the last
+# N - video_n positions are audio rows with their own (VE, abt, flow t) and target correction c
+# --------------------------------------------------------------------------------------------
+AV_CASES = [
+    dict(name="aux_av_flat_n3", shape=(1, 1, 64), video_n=40, n=3, sigma=0.6, sigma_a=0.35, corr=0.625),
+    dict(name="aux_av_flat_n0", shape=(1, 1, 64), video_n=40, n=0, sigma=0.5, sigma_a=0.2, corr=None),
+    dict(name="aux_av_channels_n4", shape=(1, 4, 48), video_n=32, n=4, sigma=0.8, sigma_a=0.55, corr=0.8),
+    dict(name="aux_av_odd_split_n2", shape=(1, 1, 37), video_n=21, n=2, sigma=0.4, sigma_a=0.3, corr=1.3),
+]
+
+
+def dump_av():
+    torch.set_num_threads(1)
+    for c in AV_CASES:
+        g = torch.Generator().manual_seed(5)
+        shape = c["shape"]
+        x, y, noise = (torch.randn(shape, generator=g) for _ in range(3))
+        mask = (torch.rand(shape, generator=g) < 0.5).float()
+        sigma = torch.tensor([c["sigma"]])
+        times = O.times_from_sigma(sigma, True)
+        sig_a = torch.tensor([c["sigma_a"]])
+        times_a = O.times_from_sigma(sig_a, True)
+        ai = torch.zeros((1, 1, shape[-1]))
+        ai[..., c["video_n"]:] = 1.0
+        corr = None if c["corr"] is None else (1.0 - ai) + c["corr"] * ai
+        tape = O.NoiseTape(generator=torch.Generator().manual_seed(3))
+        model = make_model("two_heads", True)
+        eng = RefEngine(model, NSteps=c["n"], Friction=15.0, Lambda=5.0, Beta=1.0, StepSize=0.2, IS_FLOW=True,
+                        MinStepFrac=1.0)
+        x_ref = x.clone()
+        with mock.patch.object(torch, "randn_like", tape):
+            out = eng(x_ref, y, noise, sigma, mask, tuple(times), model_options={}, seed=0, n_steps=c["n"],
+                      current_times_audio=tuple(times_a), audio_indicator=ai, audio_correction=corr)
+        # the oracle's AV path must agree with the reference bit for bit as well
+        replay = O.NoiseTape(tape.recorded)
+        hp = O.Hyper(n_steps=c["n"], min_step_frac=1.0, flow=True)
+        out_o, x_o = O.outer_step(make_model("two_heads", True), x.clone(), y, noise, sigma, mask, times, hp,
+                                  n_steps=c["n"], draw=replay, audio=O.Audio(ai, times_a, corr))
+        exact = torch.equal(out_o, out) and torch.equal(x_o, x_ref)
+        print(f"{c['name']:24s} draws {len(tape.recorded)} oracle==reference {exact}")
+        assert exact
+        meta = dict(name=c["name"], n_steps=c["n"], video_n=c["video_n"], corr=c["corr"], n_draws=len(tape.recorded))
+        np.savez_compressed(os.path.join(HERE, c["name"] + ".npz"), x=x.numpy(), y=y.numpy(), noise=noise.numpy(),
+                            sigma=sigma.numpy(), mask=mask.numpy().astype(np.uint8), ve=times.ve_sigma.numpy(),
+                            abt=times.abt.numpy(), flow_t=times.flow_t.numpy(), ve_a=times_a.ve_sigma.numpy(),
+                            abt_a=times_a.abt.numpy(), flow_a=times_a.flow_t.numpy(),
+                            tape=np.stack([d.numpy() for d in tape.recorded]) if tape.recorded else np.zeros((0,) + shape, np.float32),
+                            out=out.numpy(), x_new=x_ref.numpy(), meta=np.array(json.dumps(meta)))
+
+
+if __name__ == "__main__" and "--av" in sys.argv:
+    dump_av()

@@ -27,12 +27,12 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_native.SYMBOLS) == declared, "binding list and header drifted apart"
-    assert lib.lp_abi_version() == _native.ABI_VERSION == 2
+    assert lib.lp_abi_version() == _native.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_native.Hyper) == 40
-    assert C.sizeof(_native.Dims) == 40
+    assert C.sizeof(_native.Dims) == 48
     assert C.sizeof(_native.Rng) == 56
     assert _native.Rng.seed.offset == 24 and _native.Rng.state.offset == 48
     assert _native.TABLE_STRIDE == 32
