@@ -127,6 +127,15 @@ int lp_build_coef_table(const double* abt, const double* ve_sigma, const double*
                         const double* rep_y, const double* corr, int64_t n_rows,
                         const lp_hyper* hyper, float* table_out);
 
+/* Same table from explicit per-row half time steps (the `dtx/2`, `dty/2` a caller of the reference's
+ * `langevin_dynamics(x_t, score, mask, step_size, current_times, sigma_x, sigma_y)` controls directly,
+ * lanpaint.py:192,301-302).  scale = S per row (NULL: 1, i.e. the state stays in VP space).
+ * target_is_x0e != 0: the kernels' x0 and y inputs both carry x_t + score (an arbitrary score callback's
+ * result), so the known-region target must pass through unchanged (lam = 0 inside the target only). */
+int lp_build_coef_table_dt(const double* abt, const double* scale, const double* dt_free,
+                           const double* dt_known, double lam, int32_t target_is_x0e, int64_t n_rows,
+                           float* table_out);
+
 /* Geometry of torch's CUDA randn kernel (ATen/native/cuda/DistributionTemplates.h:
  * calc_execution_policy) for `numel` elements on `device`: grid blocks of 256
  * threads and the philox offset increment one draw consumes. */

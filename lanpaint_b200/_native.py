@@ -20,7 +20,7 @@ SUBSTEP_FIRST, SUBSTEP_FUSE_NEXT, SUBSTEP_STORE_C, SUBSTEP_MERGE_NOISE = 1, 2, 4
 
 # every symbol include/lanpaint_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = (
-    "lp_abi_version", "lp_status_string", "lp_last_cuda_error", "lp_build_coef_table",
+    "lp_abi_version", "lp_status_string", "lp_last_cuda_error", "lp_build_coef_table", "lp_build_coef_table_dt",
     "lp_torch_randn_geometry", "lp_pack_mask_f32", "lp_prologue_f32", "lp_substep_f32", "lp_substep_cfg_f32", "lp_advance_f32",
     "lp_epilogue_f32", "lp_epilogue_euler_f32", "lp_epilogue_cfg_f32", "lp_stop_stats_f32", "lp_fill_normal_f32", "lp_synth_denoiser_f32", "lp_l2_flush",
 )
@@ -71,6 +71,8 @@ def load() -> C.CDLL:
     lib.lp_last_cuda_error.argtypes = []
     lib.lp_build_coef_table.restype = i32
     lib.lp_build_coef_table.argtypes = [p, p, p, p, p, i64, C.POINTER(Hyper), p]
+    lib.lp_build_coef_table_dt.restype = i32
+    lib.lp_build_coef_table_dt.argtypes = [p, p, p, p, C.c_double, C.c_int32, i64, p]
     lib.lp_torch_randn_geometry.restype = i32
     lib.lp_torch_randn_geometry.argtypes = [i64, i32, C.POINTER(i64), C.POINTER(u64)]
     lib.lp_pack_mask_f32.restype = i32

@@ -50,42 +50,56 @@ void fill_class(float* c, double A, double g, double dt, float* sdm, float* sdmf
 
 }  // namespace
 
+namespace {
+
+// One table row from explicit per-class time steps (shared by both builders).
+void fill_row(float* t, double abt, double S, double rep_noise, double rep_y, double corr, double lam,
+              double lam_in_target, double dt_free, double dt_known) {
+  const double one_m = 1.0 - abt;
+  const double inv1m = 1.0 / one_m;
+  // lanpaint.py:313-318: A_x = 1/(1-abt), A_y = (1+Lambda)/(1-abt)
+  const double A_free = inv1m;
+  const double A_known = (1.0 + lam) * inv1m;
+  // Coef_C (lanpaint.py:217-220): C = (sqrt(abt) x0e - x_t)/(1-abt) + A x_t = c_tgt * x0e + (A - 1/(1-abt)) * x_t
+  t[LP_T_CTGT] = static_cast<float>(std::sqrt(abt) * inv1m);
+  t[LP_T_S] = static_cast<float>(S);
+  t[LP_T_INVS] = static_cast<float>(1.0 / S);
+  t[LP_T_LAM] = static_cast<float>(lam_in_target);
+  t[LP_T_ONEPLAM] = static_cast<float>(1.0 + lam_in_target);
+  t[LP_T_REPN] = static_cast<float>(rep_noise);
+  t[LP_T_REPY] = static_cast<float>(rep_y);
+  t[LP_T_CORR] = static_cast<float>(corr);
+  fill_class(t + LP_T_CLS0, A_free, 0.0, dt_free, t + LP_T_SDM, t + LP_T_SDMF);
+  fill_class(t + LP_T_CLS1, A_known, lam * inv1m, dt_known, t + LP_T_SDM + 1, t + LP_T_SDMF + 1);
+  for (int j = 28; j < LP_TABLE_STRIDE; ++j) t[j] = 0.f;
+}
+
+}  // namespace
+
 extern "C" int lp_build_coef_table(const double* abt, const double* ve_sigma, const double* rep_noise,
                                    const double* rep_y, const double* corr, int64_t n_rows,
                                    const lp_hyper* hp, float* table_out) {
   if (!abt || !ve_sigma || !hp || !table_out || n_rows < 0) return LP_ERR_INVALID;
   for (int64_t r = 0; r < n_rows; ++r) {
-    float* t = table_out + r * LP_TABLE_STRIDE;
     const double a = abt[r];
     const double one_m = 1.0 - a;
     // lanpaint.py:81  step_size = StepSize * clamp(1 - abt, min=MinStepFrac)
     const double h = hp->step_size * (one_m < hp->min_step_frac ? hp->min_step_frac : one_m);
     // lanpaint.py:301-302,185-190: dtx/2 = h * sigma_x (=1), dty/2 = h * sigma_y (=Beta)
-    const double dt_free = h;
-    const double dt_known = h * hp->beta;
-    // lanpaint.py:313-318: A_x = 1/(1-abt), A_y = (1+Lambda)/(1-abt)
-    const double inv1m = 1.0 / one_m;
-    const double A_free = inv1m;
-    const double A_known = (1.0 + hp->lam) * inv1m;
-    // Coef_C (lanpaint.py:217-220): C = (sqrt(abt) x0e - x_t)/(1-abt) + A x_t
-    //                                 = c_tgt * x0e + (A - 1/(1-abt)) * x_t
-    t[LP_T_CTGT] = static_cast<float>(std::sqrt(a) * inv1m);
-    double S;
-    if (hp->flow) {
-      S = 1.0 / (std::sqrt(a) + std::sqrt(one_m));  // lanpaint.py:97,146,163
-    } else {
-      S = std::sqrt(1.0 + ve_sigma[r] * ve_sigma[r]);  // lanpaint.py:99,148,168
-    }
-    t[LP_T_S] = static_cast<float>(S);
-    t[LP_T_INVS] = static_cast<float>(1.0 / S);
-    t[LP_T_LAM] = static_cast<float>(hp->lam);
-    t[LP_T_ONEPLAM] = static_cast<float>(1.0 + hp->lam);
-    t[LP_T_REPN] = static_cast<float>(rep_noise ? rep_noise[r] : 0.0);
-    t[LP_T_REPY] = static_cast<float>(rep_y ? rep_y[r] : 1.0);
-    t[LP_T_CORR] = static_cast<float>(corr ? corr[r] : 1.0);
-    fill_class(t + LP_T_CLS0, A_free, 0.0, dt_free, t + LP_T_SDM, t + LP_T_SDMF);
-    fill_class(t + LP_T_CLS1, A_known, hp->lam * inv1m, dt_known, t + LP_T_SDM + 1, t + LP_T_SDMF + 1);
-    for (int j = 28; j < LP_TABLE_STRIDE; ++j) t[j] = 0.f;
+    const double S = hp->flow ? 1.0 / (std::sqrt(a) + std::sqrt(one_m))          // lanpaint.py:97,146,163
+                              : std::sqrt(1.0 + ve_sigma[r] * ve_sigma[r]);       // lanpaint.py:99,148,168
+    fill_row(table_out + r * LP_TABLE_STRIDE, a, S, rep_noise ? rep_noise[r] : 0.0, rep_y ? rep_y[r] : 1.0,
+             corr ? corr[r] : 1.0, hp->lam, hp->lam, h, h * hp->beta);
   }
+  return LP_OK;
+}
+
+extern "C" int lp_build_coef_table_dt(const double* abt, const double* scale, const double* dt_free,
+                                      const double* dt_known, double lam, int32_t target_is_x0e, int64_t n_rows,
+                                      float* table_out) {
+  if (!abt || !dt_free || !dt_known || !table_out || n_rows < 0) return LP_ERR_INVALID;
+  for (int64_t r = 0; r < n_rows; ++r)
+    fill_row(table_out + r * LP_TABLE_STRIDE, abt[r], scale ? scale[r] : 1.0, 0.0, 1.0, 1.0, lam,
+             target_is_x0e ? 0.0 : lam, dt_free[r], dt_known[r]);
   return LP_OK;
 }

@@ -620,6 +620,66 @@ class LanPaint:
                             packed_mask=pm, like=like, abt_mean=float(np.float32(abt_h.astype(np.float32).mean())),
                             dims=dims)
 
+    # ---- the reference's lower-level entry point, un-fused ------------------------------------------
+    def langevin_dynamics(self, x_t, score, mask, step_size, current_times, sigma_x=1, sigma_y=0, args=None):
+        """One Langevin sub-step around an arbitrary `score(x_t)` callback, in VP space, with the
+        reference's signature and return value `(x_t, LangevinState(None, C, x0))`
+        (src/LanPaint/lanpaint.py:192-293).  Because the callback sits between the two half-advances
+        this cannot use the cross-model fusion: it runs lp_advance_f32 (first half), the callback, then
+        lp_substep_f32 (Coef_C + correction + second half) -- 2 launches instead of ~89."""
+        if args is not None and not isinstance(args, LangevinState):
+            if isinstance(args, tuple):
+                args = LangevinState(args[0], args[1], args[2] if len(args) >= 3 else None)
+        if not (isinstance(x_t, torch.Tensor) and x_t.is_cuda):
+            raise RuntimeError("lanpaint_b200.LanPaint.langevin_dynamics needs CUDA tensors")
+        lib = _native.load()
+        dev = x_t.device
+        B = x_t.shape[0]
+        if self.img_dim_size is None:
+            self.img_dim_size = x_t.ndim
+        _, abt, _ = current_times
+
+        def per_row(v):
+            t = torch.as_tensor(v, dtype=torch.float32, device=dev).reshape(-1)
+            return t if t.numel() == B else t[:1].expand(B)
+        host = torch.stack([per_row(abt), per_row(step_size), per_row(sigma_x), per_row(sigma_y)]).cpu().numpy()
+        abt_h, step_h, sx_h, sy_h = (host[k].astype(np.float64) for k in range(4))
+        dt_free, dt_known = step_h * sx_h, step_h * sy_h       # the reference's dtx/2, dty/2 (lanpaint.py:301-328)
+        if float(np.mean(dt_free.astype(np.float32))) <= 0.0:  # lanpaint.py:205
+            return x_t, args
+        table_np = np.empty((B, _native.TABLE_STRIDE), dtype=np.float32)
+        rc = lib.lp_build_coef_table_dt(_P(abt_h.ctypes.data), None, _P(dt_free.ctypes.data), _P(dt_known.ctypes.data),
+                                        C.c_double(float(self.chara_lamb)), 1, B, _P(table_np.ctypes.data))
+        _native.check(rc, "lp_build_coef_table_dt")
+        tab = torch.from_numpy(table_np).to(dev)
+        pm = mask if isinstance(mask, PackedMask) else pack_mask(mask, x_t)
+        per = x_t.numel() // B
+        dims = _native.Dims(B, per, int(np.prod(x_t.shape[2:])) if x_t.ndim > 2 else 1, pm.row_stride, pm.channel_stride)
+        stream = _P(_stream_ptr(dev))
+        xt = _f32c(x_t).clone()
+        first = args is None
+        plan = _DrawPlan(self.rng, xt, 1 if first else 2)
+        if first:
+            cbuf = torch.empty_like(xt)
+        else:
+            cbuf = _f32c(args.C).clone()
+            r = plan.rng_struct(1)
+            rc = lib.lp_advance_f32(_P(xt.data_ptr()), _P(cbuf.data_ptr()), _P(pm.data.data_ptr()), _P(tab.data_ptr()),
+                                    C.byref(dims), C.byref(r), 1, stream)
+            _native.check(rc, "lp_advance_f32")
+            self.launches += 1
+        x0e_in = _f32c(xt + score(xt))                      # Coef_C's x0 = x_t + score(x_t), lanpaint.py:218
+        x0e = torch.empty_like(xt)
+        r = plan.rng_struct(1)
+        flags = (_native.SUBSTEP_FIRST if first else 0) | _native.SUBSTEP_STORE_C
+        rc = lib.lp_substep_f32(_P(xt.data_ptr()), _P(x0e_in.data_ptr()), _P(x0e_in.data_ptr()), _P(x0e_in.data_ptr()),
+                                _P(pm.data.data_ptr()), _P(cbuf.data_ptr()), None, _P(x0e.data_ptr()),
+                                _P(tab.data_ptr()), C.byref(dims), C.byref(r), flags, stream)
+        _native.check(rc, "lp_substep_f32")
+        self.launches += 1
+        plan.finish()
+        return xt.to(x_t.dtype), LangevinState(None, cbuf, x0e)
+
     # ---- MiniMax-H3 AV flat pack: trailing audio positions on their own schedule ----------------
     def _av_split(self, ai: torch.Tensor, n_last: int) -> int:
         """Validate that the indicator marks a suffix of the last axis and return where it starts

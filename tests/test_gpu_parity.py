@@ -503,3 +503,40 @@ def test_whole_job_graph_equals_step_by_step(rng, cuda_device):
     assert e2.model_calls == e1.model_calls == 73 and e2.substeps_done == 53
     again = job.run(y, noise, m)          # a second request batch: fresh noise, same graph
     assert not torch.equal(again, got) and torch.isfinite(again).all()
+
+
+# ----------------------------------------------------------------------------
+# 7. the reference's lower-level entry point: langevin_dynamics(x_t, score, ...)
+# ----------------------------------------------------------------------------
+def test_langevin_dynamics_method_matches_oracle(cuda_device):
+    """Same call as the reference's tests/test_sho_regression.py, checked numerically against the oracle's
+    restatement of lanpaint.py:192-293 for a first and a steady sub-step with an arbitrary score callback."""
+    from lanpaint_b200.engine import NoiseTape
+    from lanpaint_b200.types import LangevinState
+    dev = cuda_device
+    torch.manual_seed(0)
+    shape = (2, 4, 16, 16)
+    x = torch.randn(shape, device=dev)
+    mask = (torch.rand(2, 1, 16, 16, device=dev) < 0.5).float().expand(shape).contiguous()
+    score = lambda z: -0.3 * z + 0.1 * torch.tanh(z)
+    abt = torch.tensor([0.5, 0.8], device=dev)
+    times = (torch.tensor([1.0, 0.5], device=dev), abt, torch.tensor([0.5, 0.3], device=dev))
+    step = torch.tensor([0.1, 0.04], device=dev).view(2, 1, 1, 1)
+    draws = [torch.randn(shape, device=dev) for _ in range(3)]
+    hp = O.Hyper(n_steps=10, friction=1.0, lam=2.0, beta=1.0, step_size=0.1)
+    ones = torch.ones(2, 1, 1, 1, device=dev)
+    tape_o = O.NoiseTape(draws)
+    x1_o, st1_o = O.langevin_substep(x, score, mask, step, O.Times(*times), hp, None, tape_o, ones, 1.5 * ones)
+    x2_o, st2_o = O.langevin_substep(x1_o, score, mask, step, O.Times(*times), hp, st1_o, tape_o, ones, 1.5 * ones)
+
+    eng = _engine(make_model("identity", False), dict(lam=2.0, step_size=0.1), rng=NoiseTape(draws))
+    eng.img_dim_size = 4
+    x1, st1 = eng.langevin_dynamics(x, score, mask, step, times, sigma_x=ones, sigma_y=1.5 * ones)
+    assert isinstance(st1, LangevinState) and st1.v is None and st1[1] is st1.C and st1[2] is st1.x0
+    x2, st2 = eng.langevin_dynamics(x1, score, mask, step, times, sigma_x=ones, sigma_y=1.5 * ones, args=st1)
+    for got, want in ((x1, x1_o), (st1.C, st1_o.C), (st1.x0, st1_o.x0), (x2, x2_o), (st2.C, st2_o.C), (st2.x0, st2_o.x0)):
+        assert max_rel(got, want) <= TIGHT
+    assert torch.isfinite(x2).all()
+    # zero step size: untouched state, like lanpaint.py:205
+    x3, st3 = eng.langevin_dynamics(x, score, mask, 0 * step, times, sigma_x=ones, sigma_y=ones)
+    assert x3 is x and st3 is None
