@@ -115,6 +115,10 @@ typedef struct lp_rng {
 int lp_abi_version(void);
 const char* lp_status_string(int status);
 int lp_last_cuda_error(void); /* cudaError_t of the last failed launch on this thread */
+/* Host-only self test of the index arithmetic the kernels rely on (the multiply-shift division that
+ * replaces `/` and `%` by per_row and spatial): returns the number of (n, d) pairs, out of `samples`
+ * pseudo-random ones plus every edge case, for which it disagrees with n / d.  0 = sound. */
+int64_t lp_selftest_index_math(int64_t samples);
 
 /* ---- host: coefficient table ------------------------------------------- */
 /* Replaces LanPaint.prepare_step_size + the mask blend of A/D/dt + the
@@ -211,6 +215,15 @@ int lp_epilogue_f32(const float* model_out, const float* y, const uint8_t* mask,
  * x_inout is the model-space state lp_substep_f32 left behind (the rewritten sampler x). */
 int lp_epilogue_euler_f32(const float* model_out, const float* y, const uint8_t* mask, float* x_inout,
                           float* out, float euler_coef, const lp_dims* dims, lp_stream_t stream);
+
+/* The boundary between two outer steps of a host-owned Euler loop in ONE pass: epilogue of step s
+ * (lanpaint.py:151-154), k-diffusion's Euler update, and the replace step of step s+1 (lanpaint.py:85-94,
+ * coefficients rep_noise/rep_y of `next_table`):
+ *   out = mask ? y : model_out ;  x = x + (x - out)*euler_coef ;  x = mask ? rep_n*noise + rep_y*y : x
+ * Known positions never read x or model_out; free positions never read noise. */
+int lp_step_boundary_f32(const float* model_out, const float* y, const float* noise, const uint8_t* mask,
+                         float* x_inout, float* out, float euler_coef, const float* next_table,
+                         const lp_dims* dims, lp_stream_t stream);
 
 /* Final denoise of an outer step straight from raw cond / uncond predictions:
  *   out = mask ? y : uncond + (cond - uncond)*cfg ;  if x_inout != NULL: x = x + (x - out)*euler_coef. */

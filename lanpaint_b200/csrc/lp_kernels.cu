@@ -687,6 +687,47 @@ __global__ void __launch_bounds__(kBlock) epilogue_cfg_kernel(const float* __res
   if (x) store_f<N>(x, i, xv);
 }
 
+template <int N>
+__global__ void __launch_bounds__(kBlock) step_boundary_kernel(const float* __restrict__ model_out,
+                                                               const float* __restrict__ y,
+                                                               const float* __restrict__ noise,
+                                                               const uint8_t* __restrict__ mask, float* x, float* out,
+                                                               float coef, const float* __restrict__ next_table,
+                                                               Geometry g) {
+  const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
+  if (i >= g.total) return;
+  uint32_t row, mi;
+  locate(g, i, row, mi);
+  bool known[N];
+  load_m<N>(mask, mi, known);
+  bool any_known = false, any_free = false;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    any_known |= known[j];
+    any_free |= !known[j];
+  }
+  float ov[N], yv[N], xv[N], nv[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) ov[j] = xv[j] = nv[j] = 0.f;
+  load_f_ro<N>(y, i, yv);
+  if (any_free) {  // free positions: denoised output and the running state
+    load_f_ro<N>(model_out, i, ov);
+    load_f<N>(x, i, xv);
+  }
+  if (any_known) load_f_ro<N>(noise, i, nv);  // known positions: re-noised copy of the clean latent
+  const float rn = __ldg(next_table + (size_t)row * LP_TABLE_STRIDE + LP_T_REPN);
+  const float ry = __ldg(next_table + (size_t)row * LP_TABLE_STRIDE + LP_T_REPY);
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const float o = known[j] ? yv[j] : ov[j];
+    const float stepped = fmaf(xv[j] - o, coef, xv[j]);
+    ov[j] = o;
+    xv[j] = known[j] ? fmaf(rn, nv[j], ry * yv[j]) : stepped;
+  }
+  store_f<N>(out, i, ov);
+  store_f<N>(x, i, xv);
+}
+
 __global__ void __launch_bounds__(kBlock) pack_mask_kernel(const float* __restrict__ m, uint8_t* out,
                                                            uint32_t n, int invert) {
   const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
@@ -853,6 +894,33 @@ extern "C" const char* lp_status_string(int status) {
 
 extern "C" int lp_last_cuda_error(void) { return g_last_cuda_error; }
 
+extern "C" int64_t lp_selftest_index_math(int64_t samples) {
+  int64_t bad = 0;
+  auto check = [&](uint32_t n, uint32_t d) {
+    const FastDiv f = make_fastdiv(d);
+    const uint32_t q = f.mul ? (uint32_t)((((uint64_t)n * f.mul) >> 32) >> f.shift) : n;  // == FastDiv::div
+    if (q != n / d) ++bad;
+  };
+  const uint32_t ds[] = {1u, 2u, 3u, 4u, 5u, 7u, 35u, 105u, 1024u, 3600u, 16384u, 65536u, 75600u, 1209600u,
+                         (1u << 30), (1u << 31) - 1u, 0x7fffffffu, 1000003u};
+  const uint32_t ns[] = {0u, 1u, 2u, 3u, 1023u, 65535u, 65536u, (1u << 31) - 1u, (1u << 31) - 2u, 0x40000000u};
+  for (uint32_t d : ds)
+    for (uint32_t n : ns) {
+      check(n, d);
+      if (d > 1 && n >= d) { check(n - n % d, d); check(n - n % d - 1, d); }
+    }
+  uint64_t st = 0x9E3779B97F4A7C15ull;
+  for (int64_t k = 0; k < samples; ++k) {
+    st = st * 6364136223846793005ull + 1442695040888963407ull;
+    const uint32_t n = (uint32_t)(st >> 33);                       // < 2^31
+    st = st * 6364136223846793005ull + 1442695040888963407ull;
+    uint32_t d = (uint32_t)(st >> 33) >> ((st >> 20) & 31);        // all magnitudes
+    if (d == 0) d = 1;
+    check(n, d);
+  }
+  return bad;
+}
+
 extern "C" int lp_torch_randn_geometry(int64_t numel, int device, int64_t* grid_out, uint64_t* increment_out) {
   return torch_grid(numel, device, grid_out, increment_out);
 }
@@ -961,6 +1029,21 @@ extern "C" int lp_substep_cfg_f32(float* x_model, const float* cond, const float
   if (!uncond || uncond == cond) return LP_ERR_INVALID;
   return substep_impl(x_model, cond, uncond, y, mask, c_state, x_copy, x0e_out, table, dims, rng, flags, stream, 1,
                       cfg, cfg_big);
+}
+
+extern "C" int lp_step_boundary_f32(const float* model_out, const float* y, const float* noise, const uint8_t* mask,
+                                    float* x_inout, float* out, float euler_coef, const float* next_table,
+                                    const lp_dims* dims, lp_stream_t stream) {
+  if (!model_out || !y || !noise || !mask || !x_inout || !out || !next_table) return LP_ERR_INVALID;
+  Geometry g;
+  if (int rc = make_geometry(dims, g)) return rc;
+  if (g.total == 0) return LP_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool v4 = geometry_vec4(g, mask) && aligned16(model_out) && aligned16(y) && aligned16(noise) &&
+                  aligned16(x_inout) && aligned16(out);
+  if (v4) step_boundary_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(model_out, y, noise, mask, x_inout, out, euler_coef, next_table, g);
+  else step_boundary_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(model_out, y, noise, mask, x_inout, out, euler_coef, next_table, g);
+  return check_launch();
 }
 
 extern "C" int lp_epilogue_cfg_f32(const float* cond, const float* uncond, float cfg, const float* y,

@@ -387,7 +387,8 @@ class LanPaint:
 
     # ---- the launch sequence of one outer step (shared by the eager path and graph capture) ----
     def _launch_sequence(self, xm, y, nz, pm, dims, tab, t_model, sigma_dev, cbuf, out, active, plan, call_scaling,
-                         model_options, seed, stopper, rng_state, euler_coef=None):
+                         model_options, seed, stopper, rng_state, euler_coef=None, skip_prologue=False,
+                         next_table=None):
         lib = _native.load()
         dev = xm.device
         stream = _P(_stream_ptr(dev))
@@ -396,12 +397,14 @@ class LanPaint:
         if call_scaling:  # opaque noise_scaling: call it like the reference does (lanpaint.py:88)
             sampling = self.inner_model.inner_model.model_sampling
             noise_arg = _f32c(sampling.noise_scaling(self.add_none_dims(sigma_dev), nz, y))
-        # prologue: replace step + change of variables (lanpaint.py:85-99)
-        rc = lib.lp_prologue_f32(_P(xm.data_ptr()), _P(y.data_ptr()), _P(noise_arg.data_ptr()),
-                                 _P(pm.data.data_ptr()), _P(xm.data_ptr()), None, _P(tab.data_ptr()),
-                                 C.byref(dims), stream)
-        _native.check(rc, "lp_prologue_f32")
-        self.launches += 1
+        # prologue: replace step + change of variables (lanpaint.py:85-99); a host-owned Euler loop has
+        # already applied it inside the previous step's lp_step_boundary_f32
+        if not skip_prologue:
+            rc = lib.lp_prologue_f32(_P(xm.data_ptr()), _P(y.data_ptr()), _P(noise_arg.data_ptr()),
+                                     _P(pm.data.data_ptr()), _P(xm.data_ptr()), None, _P(tab.data_ptr()),
+                                     C.byref(dims), stream)
+            _native.check(rc, "lp_prologue_f32")
+            self.launches += 1
         done = 0
         for i in range(active):
             first = i == 0
@@ -490,6 +493,13 @@ class LanPaint:
             return done
         mo, _ = self.unpack_model_output(out_heads)
         mo = _as_operand(mo, xm)
+        if next_table is not None and euler_coef is not None:
+            rc = lib.lp_step_boundary_f32(_P(mo.data_ptr()), _P(y.data_ptr()), _P(nz.data_ptr()),
+                                          _P(pm.data.data_ptr()), _P(xm.data_ptr()), _P(out.data_ptr()),
+                                          C.c_float(euler_coef), _P(next_table.data_ptr()), C.byref(dims), stream)
+            _native.check(rc, "lp_step_boundary_f32")
+            self.launches += 1
+            return done
         if euler_coef is None:
             rc = lib.lp_epilogue_f32(_P(mo.data_ptr()), _P(y.data_ptr()), _P(pm.data.data_ptr()), _P(out.data_ptr()),
                                      C.byref(dims), stream)

@@ -247,9 +247,12 @@ class GraphedJob:
         state = self.rng_state.data_ptr()
         for i, st in enumerate(self.sched.steps):
             coef = (st.sigma_next - st.sigma) / st.sigma
+            last = i + 1 == len(self.sched.steps)
             eng._launch_sequence(self.x, self.y, self.noise, pm, dims, self.tables[i], self.t_model[i], self.sigma[i],
                                  self.c, self.out, self.active[i], plan, False, None, 0, None, state,
-                                 euler_coef=coef if self.fused_euler else None)
+                                 euler_coef=coef if self.fused_euler else None,
+                                 skip_prologue=self.fused_euler and i > 0,
+                                 next_table=self.tables[i + 1] if (self.fused_euler and not last) else None)
             if not self.fused_euler:
                 self.x.add_(self.x - self.out, alpha=coef)
 

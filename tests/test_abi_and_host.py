@@ -38,6 +38,11 @@ def test_struct_layouts_match_header():
     assert _native.TABLE_STRIDE == 32
 
 
+def test_index_math_selftest():
+    """multiply-shift division used for (row, channel, site) decomposition is exact for every n < 2^31"""
+    assert _native.load().lp_selftest_index_math(2_000_000) == 0
+
+
 def test_status_strings():
     lib = _native.load()
     assert lib.lp_status_string(0) == b"ok"

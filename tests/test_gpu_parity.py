@@ -540,3 +540,45 @@ def test_langevin_dynamics_method_matches_oracle(cuda_device):
     # zero step size: untouched state, like lanpaint.py:205
     x3, st3 = eng.langevin_dynamics(x, score, mask, 0 * step, times, sigma_x=ones, sigma_y=ones)
     assert x3 is x and st3 is None
+
+
+def test_graph_capture_of_a_torch_module_denoiser(cuda_device):
+    """The model call stays ordinary PyTorch code (here a small conv net with two heads and a sigma
+    embedding); the engine captures it together with its own kernels and replays the graph."""
+    dev = cuda_device
+
+    class TinyNet(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(0)
+            self.c1 = torch.nn.Conv2d(4, 32, 3, padding=1)
+            self.c2 = torch.nn.Conv2d(32, 8, 3, padding=1)
+            for p in self.parameters():
+                p.data = torch.randn(p.shape, generator=g) * 0.05
+            self.inner_model = self
+            self.model_sampling = O.VESampling()
+
+        def forward(self, x, sigma, model_options=None, seed=None):
+            emb = (1.0 / (1.0 + sigma ** 2)).view(-1, 1, 1, 1)
+            h = torch.nn.functional.silu(self.c1(x * emb))
+            o = self.c2(h)
+            return x * emb + o[:, :4], x * emb + o[:, 4:]
+
+    net = TinyNet().to(dev).eval()
+    shape = (2, 4, 32, 32)
+    x, y, noise, m = synth_inputs(shape, seed=13, device=dev)
+    res = {}
+    with torch.no_grad():
+        for mode in (False, True):
+            torch.manual_seed(21)
+            eng = _engine(net, dict(n_steps=3), rng="philox", cuda_graph=mode, batched_replace="per_sample")
+            xx = x.clone()
+            outs = []
+            for sv in (5.0, 1.5):
+                sig = torch.full((2,), sv)
+                outs.append(eng(xx, y, noise, sig, m, tuple(O.times_from_sigma(sig, False)), None, 0, n_steps=3))
+            res[mode] = (outs, xx, eng)
+    assert len([g for g in res[True][2]._graphs.values() if g]) == 1
+    for a, b in zip(res[False][0], res[True][0]):
+        assert max_rel(a, b) <= 1e-5
+    assert max_rel(res[False][1], res[True][1]) <= 1e-5
