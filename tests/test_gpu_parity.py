@@ -555,8 +555,6 @@ def test_graph_capture_of_a_torch_module_denoiser(cuda_device):
             self.c2 = torch.nn.Conv2d(32, 8, 3, padding=1)
             for p in self.parameters():
                 p.data = torch.randn(p.shape, generator=g) * 0.05
-            self.inner_model = self
-            self.model_sampling = O.VESampling()
 
         def forward(self, x, sigma, model_options=None, seed=None):
             emb = (1.0 / (1.0 + sigma ** 2)).view(-1, 1, 1, 1)
@@ -564,7 +562,16 @@ def test_graph_capture_of_a_torch_module_denoiser(cuda_device):
             o = self.c2(h)
             return x * emb + o[:, :4], x * emb + o[:, 4:]
 
-    net = TinyNet().to(dev).eval()
+    class Guider:   # the engine-seam protocol around the module (what ComfyUI's CFGGuider is)
+        def __init__(self, module):
+            self.module = module
+            self.inner_model = self
+            self.model_sampling = O.VESampling()
+
+        def __call__(self, x, sigma, model_options=None, seed=None):
+            return self.module(x, sigma)
+
+    net = Guider(TinyNet().to(dev).eval())
     shape = (2, 4, 32, 32)
     x, y, noise, m = synth_inputs(shape, seed=13, device=dev)
     res = {}
