@@ -250,6 +250,17 @@ int lp_fill_normal_f32(float* out, int64_t n, const lp_rng* rng, lp_stream_t str
 int lp_synth_denoiser_f32(const float* x, float* h0, float* h1, int64_t n, const float* coef5_host,
                           lp_stream_t stream);
 
+/* L2 residency for the operands every sub-step re-reads (the clean latent y and the mask: 4 + 1/C of the
+ * 28 + 1/C bytes per element).  B200 has 126 MB of L2; pinning y (and the mask that follows it in the same
+ * allocation, if any) with a persisting access-policy window turns those reads into L2 hits for the whole
+ * job.  lp_l2_persist_set() raises cudaLimitPersistingL2CacheSize to cover `bytes` (clamped to the device
+ * maximum; hit_ratio is scaled down accordingly) and installs the window on `stream`: every kernel launched
+ * (or captured) on that stream afterwards carries it.  lp_l2_persist_clear() removes the window and resets the
+ * persisting lines.  Both are host-side configuration calls, not captured operations. */
+int lp_l2_persist_capacity(int device, size_t* max_persisting_bytes, size_t* max_window_bytes);
+int lp_l2_persist_set(const void* ptr, size_t bytes, lp_stream_t stream);
+int lp_l2_persist_clear(lp_stream_t stream);
+
 /* Writes `bytes` of scratch (> L2) to evict the working set between launches. */
 int lp_l2_flush(void* scratch, size_t bytes, lp_stream_t stream);
 
