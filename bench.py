@@ -251,7 +251,7 @@ def run_b200(args):
     pm = pack_mask(mask, y)
     torch.manual_seed(1000 + rank)
 
-    gjob = GraphedJob(eng, sched, (R,) + SHAPE, dev, l2_persist=not args.no_l2_persist) if args.launch == "job-graph" else None
+    gjob = GraphedJob(eng, sched, (R,) + SHAPE, dev, l2_persist=args.l2_persist) if args.launch == "job-graph" else None
 
     def job():
         if gjob is not None:
@@ -336,7 +336,7 @@ def run_b200(args):
             lanes.append({"in": (hy, hn, hm), "out": torch.empty((R,) + SHAPE).pin_memory(),
                           "stream": torch.cuda.Stream(device=dev),
                           "job": GraphedJob(make_engine(False), sched, (R,) + SHAPE, dev,
-                                            l2_persist=not args.no_l2_persist) if gjob is not None else None})
+                                            l2_persist=args.l2_persist) if gjob is not None else None})
         bi = sum(t.numel() * 4 for t in lanes[0]["in"])
         bo = lanes[0]["out"].numel() * 4
 
@@ -408,7 +408,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-kernel-timer", dest="kernel_timer", action="store_false")
-    ap.add_argument("--no-l2-persist", action="store_true", help="do not pin the clean latent in L2")
+    ap.add_argument("--l2-persist", action="store_true", help="pin the clean latent in L2 (measured slower; off)")
     ap.add_argument("--launch", default="job-graph", choices=["job-graph", "step-graph", "eager"],
                     help="one CUDA graph per job (default) | one per outer step | plain launches")
     args = ap.parse_args()

@@ -1211,6 +1211,7 @@ extern "C" int lp_l2_persist_clear(lp_stream_t stream) {
   v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
   cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &v);
   if (cudaCtxResetPersistingL2Cache() != cudaSuccess) return check_launch() ? LP_ERR_CUDA : LP_ERR_CUDA;
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);  // give the set-aside back to normal traffic
   return LP_OK;
 }
 
