@@ -589,3 +589,65 @@ def test_graph_capture_of_a_torch_module_denoiser(cuda_device):
     for a, b in zip(res[False][0], res[True][0]):
         assert max_rel(a, b) <= 1e-5
     assert max_rel(res[False][1], res[True][1]) <= 1e-5
+
+
+# ----------------------------------------------------------------------------
+# 8. randomized configurations (seeded): shapes, mask layouts, head aliasing, schedules, hyper-parameters
+# ----------------------------------------------------------------------------
+def _random_cases(n, seed=20260922):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for k in range(n):
+        ndim = int(rng.choice([3, 4, 4, 4, 5]))
+        B = int(rng.choice([1, 1, 2, 3]))
+        Cc = int(rng.choice([1, 3, 4, 16]))
+        sp = tuple(int(v) for v in rng.choice([2, 3, 4, 5, 8, 12, 16], size=ndim - 2))
+        flow = bool(rng.random() < 0.4)
+        sigma = [float(rng.uniform(0.05, 0.98) if flow else np.exp(rng.uniform(np.log(0.03), np.log(14.6)))) for _ in range(B)]
+        if rng.random() < 0.5:
+            sigma = [sigma[0]] * B
+        cases.append(dict(id=k, shape=(B, Cc) + sp, flow=flow, sigma=sigma, n=int(rng.integers(0, 7)),
+                          model=str(rng.choice(["identity", "two_heads", "bare", "one_tuple"])),
+                          mask=str(rng.choice(["full", "chan", "batch1", "all0", "all1"])),
+                          lam=float(rng.choice([0.1, 1.0, 5.0, 12.0])), beta=float(rng.choice([1.0, 0.5, 2.0])),
+                          step=float(rng.choice([0.05, 0.2, 0.6])), min_frac=float(rng.choice([0.0, 0.3, 1.0])),
+                          noncontig=bool(rng.random() < 0.2)))
+    return cases
+
+
+@pytest.mark.parametrize("c", _random_cases(48), ids=lambda c: f"r{c['id']}")
+def test_randomized_configurations_match_oracle(c, cuda_device):
+    from lanpaint_b200.engine import NoiseTape
+    dev = cuda_device
+    shape = c["shape"]
+    g = torch.Generator().manual_seed(1000 + c["id"])
+    x, y, noise = (torch.randn(shape, generator=g).to(dev) for _ in range(3))
+    B, Cc = shape[0], shape[1]
+    if c["mask"] == "all0":
+        m = torch.zeros((B, 1) + shape[2:])
+    elif c["mask"] == "all1":
+        m = torch.ones((B, 1) + shape[2:])
+    elif c["mask"] == "batch1":
+        m = (torch.rand((1, 1) + shape[2:], generator=g) < 0.5).float()
+    elif c["mask"] == "chan":
+        m = (torch.rand((B, 1) + shape[2:], generator=g) < 0.5).float()
+    else:
+        m = (torch.rand(shape, generator=g) < 0.5).float()     # genuinely channel-dependent mask
+    m = m.to(dev)
+    mask_full = m.expand(shape).contiguous()
+    sig = torch.tensor(c["sigma"], device=dev)
+    times = O.times_from_sigma(sig, c["flow"])
+    hp = O.Hyper(n_steps=c["n"], lam=c["lam"], beta=c["beta"], step_size=c["step"], min_step_frac=c["min_frac"],
+                 flow=c["flow"])
+    tape = O.NoiseTape(generator=torch.Generator().manual_seed(c["id"]))
+    out_o, x_o = O.outer_step(make_model(c["model"], c["flow"]), x.clone(), y, noise, sig, mask_full, times, hp,
+                              n_steps=c["n"], draw=tape)
+    eng = _engine(make_model(c["model"], c["flow"]),
+                  dict(n_steps=c["n"], lam=c["lam"], beta=c["beta"], step_size=c["step"], min_step_frac=c["min_frac"],
+                       flow=c["flow"]), rng=NoiseTape(tape.recorded))
+    xe = x.clone()
+    if c["noncontig"] and xe.ndim >= 4:
+        xe = xe.transpose(-1, -2).contiguous().transpose(-1, -2)
+    out_e = eng(xe, y, noise, sig, m, tuple(times), {}, 0, n_steps=c["n"])
+    tol = TIGHT * (10 if min(c["sigma"]) < 0.06 and not c["flow"] else 1)   # 1-abt ~ 1e-3: the reference's own
+    assert max_rel(out_e, out_o) <= tol and max_rel(xe, x_o) <= tol, c       # cancellation noise grows there
