@@ -199,7 +199,9 @@ def workload_config(args):
     return {"workload": "sdxl_1024_inpaint_4x128x128_karras20_N5", "requests_per_gpu": args.requests,
             "latent_shape": [1] + list(SHAPE), "outer_steps": N_OUTER, "think_steps": N_INNER,
             "substeps_per_request": 53, "model_calls_per_request": 73, "denoiser": "synthetic pointwise two-head",
-            "sampler": "euler", "mask": "random 50% per spatial site", "rng": args.rng,
+            "sampler": "euler",
+            "mask": "random 50% per spatial site" if args.mask == "random" else "centred 90x90 hole (49.4% unknown)",
+            "rng": args.rng,
             "launch": {"job-graph": "one CUDA graph per job (20 outer steps), replayed per request batch",
                        "step-graph": "one CUDA graph per outer step", "eager": "plain launches"}[args.launch],
             "parallelism": f"replicas x{args.gpus} (requests sharded, no data-path collective)",
@@ -210,12 +212,19 @@ def workload_config(args):
 # ------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------
+MASK_KIND = "random"
+
+
 def make_inputs(requests, dev, seed, pinned=False):
     g = torch.Generator().manual_seed(seed)
     shape = (requests,) + SHAPE
     y = torch.randn(shape, generator=g)
     noise = torch.randn(shape, generator=g)
-    mask = (torch.rand((requests, 1) + SHAPE[1:], generator=g) < 0.5).float()  # 1 = known
+    if MASK_KIND == "blob":   # a real inpainting mask: known everywhere except one centred 90x90 hole (49.4 %)
+        mask = torch.ones((requests, 1) + SHAPE[1:])
+        mask[:, :, 19:109, 19:109] = 0.0
+    else:                     # rand(B,1,H,W) < 0.5 per spatial site (worst case for operand skipping)
+        mask = (torch.rand((requests, 1) + SHAPE[1:], generator=g) < 0.5).float()  # 1 = known
     if pinned:
         return [t.pin_memory() for t in (y, noise, mask)]
     return [t.to(dev) for t in (y, noise, mask)]
@@ -411,7 +420,11 @@ def main():
     ap.add_argument("--l2-persist", action="store_true", help="pin the clean latent in L2 (measured slower; off)")
     ap.add_argument("--launch", default="job-graph", choices=["job-graph", "step-graph", "eager"],
                     help="one CUDA graph per job (default) | one per outer step | plain launches")
+    ap.add_argument("--mask", default="random", choices=["random", "blob"],
+                    help="random 50%% per site (SURVEY 8d, default) | one centred hole of the same area")
     args = ap.parse_args()
+    global MASK_KIND
+    MASK_KIND = args.mask
     if args.impl == "reference":
         run_reference(args)
     else:

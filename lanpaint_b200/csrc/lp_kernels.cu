@@ -283,11 +283,32 @@ __device__ __forceinline__ void substep_vector(const SubstepArgs& a, uint32_t i,
   locate(a.g, i, row, mi);
   float x[N], x0[N], x0b[N], y[N], cp[N], cn[N], te[N];
   bool known[N];
+  // The mask decides which operands this vector needs: free positions use only x0, known positions only
+  // x0_big and y (score_model, lanpaint.py:182-184).  Inpainting masks are spatially coherent, so most
+  // vectors are all-free or all-known and skip 4-8 of their 20 input bytes per element.
+  load_m<N>(a.mask, mi, known);
   load_f<N>(a.x, i, x);
-  load_f_ro<N>(a.x0, i, x0);
-  if (a.x0b != a.x0) {
-    load_f_ro<N>(a.x0b, i, x0b);
+  if (!kFirst) {
+    load_f<N>(a.c, i, cp);
   } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) cp[j] = 0.f;
+  }
+  bool any_known = false, any_free = false;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    any_known |= known[j];
+    any_free |= !known[j];
+  }
+  const bool aliased = a.x0b == a.x0;
+  const bool need_x0 = any_free || aliased || a.use_cfg;
+  const bool need_x0b = (any_known || a.use_cfg) && !aliased;
+#pragma unroll
+  for (int j = 0; j < N; ++j) x0[j] = x0b[j] = y[j] = 0.f;
+  if (need_x0) load_f_ro<N>(a.x0, i, x0);
+  if (need_x0b) {
+    load_f_ro<N>(a.x0b, i, x0b);
+  } else if (aliased) {
 #pragma unroll
     for (int j = 0; j < N; ++j) x0b[j] = x0[j];
   }
@@ -299,14 +320,7 @@ __device__ __forceinline__ void substep_vector(const SubstepArgs& a, uint32_t i,
       x0b[j] = __fadd_rn(u, __fmul_rn(d, a.cfg_big));
     }
   }
-  load_f_ro<N>(a.y, i, y);
-  load_m<N>(a.mask, mi, known);
-  if (!kFirst) {
-    load_f<N>(a.c, i, cp);
-  } else {
-#pragma unroll
-    for (int j = 0; j < N; ++j) cp[j] = 0.f;
-  }
+  if (any_known) load_f_ro<N>(a.y, i, y);
   RowCoef<kFirst, kNext> t;
   t.load(a.table + (size_t)row * LP_TABLE_STRIDE);
 #pragma unroll

@@ -18,12 +18,18 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--requests", type=int, default=128)
 ap.add_argument("--rng", default="philox")
 ap.add_argument("--no-merge", action="store_true")
+ap.add_argument("--mask", default="random", choices=["random", "blob"])
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 shape = (args.requests, 4, 128, 128)
 g = torch.Generator().manual_seed(0)
 y = torch.randn(shape, generator=g).to(dev)
-mask = (torch.rand((args.requests, 1, 128, 128), generator=g) < 0.5).float().to(dev)
+if args.mask == "blob":
+    mask = torch.ones((args.requests, 1, 128, 128))
+    mask[:, :, 19:109, 19:109] = 0.0
+    mask = mask.to(dev)
+else:
+    mask = (torch.rand((args.requests, 1, 128, 128), generator=g) < 0.5).float().to(dev)
 eng = LanPaint(SynthDenoiser(VESampling()), 5, 15.0, 5.0, 1.0, 0.2, MinStepFrac=1.0, rng=args.rng,
                merge_noise=not args.no_merge)
 ts = time_steady_substep(eng, y, pack_mask(mask, y), sigma=2.0, launches=53, repeats=5)
