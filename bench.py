@@ -334,6 +334,25 @@ def run_b200(args):
         if os.path.exists(tr):
             roof["traffic"] = json.load(open(tr)).get(str(R))
 
+    if args.kernel_timer and rank == 0:
+        # context for the fraction above: the same copy probe MEASURED_PEAKS.json was produced with
+        # (torch b.copy_(a) over 1 Gi bf16 elements, read+write bytes, best of 10), on THIS box
+        try:
+            a_ = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+            b_ = torch.empty_like(a_)
+            best = float("inf")
+            for _ in range(10):
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                b_.copy_(a_)
+                c1.record()
+                c1.synchronize()
+                best = min(best, c0.elapsed_time(c1))
+            roof["copy_gbs_this_box"] = 2 * a_.numel() * 2 / (best * 1e-3) / 1e9
+            del a_, b_
+        except Exception:
+            pass
+
     # ---- e2e: host buffers in, host result out, through the public call; copies inside the timed region.
     # Two request batches are in flight on two streams (each with its own pinned buffers and job graph), so
     # the H2D of batch k+1 and the D2H of batch k-1 overlap the kernels of batch k, as a serving loop does.
