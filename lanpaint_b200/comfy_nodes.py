@@ -38,7 +38,7 @@ try:  # WAN22 exists only in recent ComfyUI builds
 except Exception:  # pragma: no cover
     WAN22 = None
 
-from .engine import CfgPair, LanPaint, pack_mask
+from .engine import CfgPair, LanPaint, _IdentityCache, pack_mask
 from .schedule import effective_inner_steps, min_step_frac_effective_steps, times_from_sigma  # noqa: F401
 
 FLOW_MODEL_TYPES = (ModelType.FLOW, getattr(ModelType, "FLOW_AV", None))
@@ -226,21 +226,20 @@ class KSamplerX0Inpaint:
         self.sigmas_host = [float(v) for v in (host if host is not None else sigmas.detach().cpu())]
         self.audio_indicator = None
         self.audio_shifts = None
-        self._mask_key = None
-        self._packed = None
+        self._mask_cache = _IdentityCache()
 
     def _latent_mask(self, denoise_mask, like):
         """1 - (denoise_mask > 0.5), packed once per distinct mask tensor (nodes.py:281-283)."""
-        key = (denoise_mask.data_ptr(), denoise_mask._version, tuple(denoise_mask.shape))
-        if key != self._mask_key:
+        packed = self._mask_cache.get(denoise_mask)
+        if packed is None:
             known = denoise_mask <= 0.5
             # prepare_mask repeats one spatial mask over the channels; if so keep a single copy
             # (1/C byte per latent element).  One sync per distinct mask tensor, not per outer step.
             if known.ndim == like.ndim and known.shape[1] > 1 and bool((known == known[:, :1]).all()):
                 known = known[:, :1]
-            self._packed = pack_mask(known, like)
-            self._mask_key = key
-        return self._packed
+            packed = pack_mask(known, like)
+            self._mask_cache.put(denoise_mask, packed)
+        return packed
 
     def __call__(self, x, sigma, denoise_mask, model_options={}, seed=None, **kwargs):
         mtype = self.inner_model.inner_model.model_type

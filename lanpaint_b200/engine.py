@@ -132,23 +132,44 @@ def pack_mask(latent_mask: torch.Tensor, like: torch.Tensor) -> PackedMask:
     return PackedMask(data, Cc * spatial, spatial)
 
 
+def _tensor_key(t: torch.Tensor):
+    """What can change under us without the object changing: storage address, layout, in-place writes.
+    Inference tensors (ComfyUI runs nodes under torch.inference_mode) have no version counter."""
+    try:
+        version = t._version
+    except RuntimeError:
+        version = None
+    return (t.data_ptr(), version, tuple(t.shape), tuple(t.stride()), t.dtype)
+
+
+class _Ident:
+    """Identity of a tensor for caching: the SAME Python object (a freed tensor's address is routinely
+    handed to a new one by the caching allocator) in the same state."""
+
+    __slots__ = ("ref", "key")
+
+    def __init__(self, t: torch.Tensor):
+        self.ref = weakref.ref(t)
+        self.key = _tensor_key(t)
+
+    def matches(self, t: torch.Tensor) -> bool:
+        return self.ref() is t and self.key == _tensor_key(t)
+
+
 class _IdentityCache:
-    """value cached per (tensor identity, version): avoids recomputing per outer step."""
+    """value cached per tensor identity: avoids recomputing per outer step."""
 
     def __init__(self):
-        self._key = None
-        self._ref = None
+        self._ident: Optional[_Ident] = None
         self.value = None
 
     def get(self, t: torch.Tensor):
-        key = (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype)
-        if self._key == key and self._ref is not None and self._ref() is t:
+        if self._ident is not None and self._ident.matches(t):
             return self.value
         return None
 
     def put(self, t: torch.Tensor, value):
-        self._key = (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype)
-        self._ref = weakref.ref(t)
+        self._ident = _Ident(t)
         self.value = value
 
 
@@ -561,13 +582,12 @@ class LanPaint:
             self._graph_statics = {key: st}
             self._graphs = {}
         for slot, (name, src) in enumerate((("y", y), ("nz", nz), ("mask", pm.data))):
-            ident = (src.data_ptr(), src._version, tuple(src.shape))
-            if st["src"][slot] != ident:
+            if st["src"][slot] is None or not st["src"][slot].matches(src):
                 if st[name].shape != src.shape:
                     st[name] = torch.empty_like(src)
                     self._graphs = {}
                 st[name].copy_(src)
-                st["src"][slot] = ident
+                st["src"][slot] = _Ident(src)
         return st
 
     def _capture(self, key, st, dims, B, host, sigma_shape, active, plan, call_scaling, model_options, seed):

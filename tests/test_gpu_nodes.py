@@ -144,3 +144,26 @@ def test_post_cfg_hook_disables_the_fusion(cuda_device):
     assert isinstance(hooked, tuple) and torch.equal(hooked[0], h0) and torch.equal(hooked[1], h1)
     cfg1 = N.sampling_function_LanPaint(model, x, t, -0.2, 0.3, 1.0, 1.0, model_options={})
     assert isinstance(cfg1, tuple)   # uncond skipped at cfg == 1: nothing to fuse
+
+
+def test_nodes_run_under_inference_mode(cuda_device):
+    """ComfyUI executes nodes under torch.inference_mode(): inference tensors have no version counter and
+    cannot be mutated outside it -- the caches and the in-place contract must cope."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    dev = cuda_device
+    g = torch.Generator().manual_seed(2)
+    y = torch.randn(1, 4, 32, 32, generator=g)
+    noise_mask = (torch.rand(1, 1, 32, 32, generator=g) < 0.5).float()
+
+    def run():
+        patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+        (out,) = N.LanPaint_KSampler().sample(patcher, 5, 8, 4.0, "euler", "karras", 0.3, -0.2,
+                                              {"samples": y, "noise_mask": noise_mask}, 1.0, 3, "Image First", "",
+                                              N.IMAGE_MODE)
+        return out["samples"]
+
+    plain = run()
+    with torch.inference_mode():
+        inf = run()
+    assert torch.equal(plain, inf.clone())

@@ -651,3 +651,29 @@ def test_randomized_configurations_match_oracle(c, cuda_device):
     out_e = eng(xe, y, noise, sig, m, tuple(times), {}, 0, n_steps=c["n"])
     tol = TIGHT * (10 if min(c["sigma"]) < 0.06 and not c["flow"] else 1)   # 1-abt ~ 1e-3: the reference's own
     assert max_rel(out_e, out_o) <= tol and max_rel(xe, x_o) <= tol, c       # cancellation noise grows there
+
+
+def test_graph_statics_follow_the_tensor_not_the_address(cuda_device):
+    """The caching allocator hands a freed tensor's address to the next one: operand caches must key on the
+    tensor object, or a new request would silently reuse the previous request's clean latent."""
+    from lanpaint_b200.runner import SynthDenoiser, VESampling
+    dev = cuda_device
+    shape = (2, 4, 32, 32)
+    x, _, noise, m = synth_inputs(shape, seed=3, device=dev)
+    sig = torch.full((2,), 2.0)
+    times = tuple(O.times_from_sigma(sig, False))
+
+    def run(eng, y):
+        torch.manual_seed(1)
+        return eng(x.clone(), y, noise, sig, m, times, None, 0, n_steps=3)
+
+    eng = _engine(SynthDenoiser(VESampling()), dict(n_steps=3), rng="philox", cuda_graph=True, batched_replace="per_sample")
+    y1 = torch.randn(shape, device=dev)
+    out1 = run(eng, y1)
+    ptr = y1.data_ptr()
+    del y1
+    y2 = torch.randn(shape, device=dev) + 3.0
+    same_address = y2.data_ptr() == ptr
+    out2 = run(eng, y2)
+    want = run(_engine(SynthDenoiser(VESampling()), dict(n_steps=3), rng="philox", batched_replace="per_sample"), y2)
+    assert torch.equal(out2, want) and not torch.equal(out1, out2), f"stale operand (same address: {same_address})"
