@@ -10,6 +10,7 @@
 // memory round trip, no host synchronisation, graph-capturable.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "lanpaint_b200.h"
 
@@ -18,6 +19,40 @@ namespace lp {
 thread_local int g_last_cuda_error = 0;
 
 constexpr int kBlock = 256;
+
+// Programmatic dependent launch: every kernel below starts with pdl_prologue() -- wait until the grid it
+// depends on has completed and flushed (griddepcontrol.wait), then let the NEXT kernel of the stream begin
+// launching (griddepcontrol.launch_dependents) -- and every launch goes through launch_kernel(), which sets
+// cudaLaunchAttributeProgrammaticStreamSerialization.  Inside a captured job (146 small dependent kernels)
+// this hides most of the launch latency between consecutive nodes; it never relaxes ordering, because each
+// dependent still waits for its predecessor to finish before touching memory.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("LANPAINT_B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ----------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011; same constants/round structure as cuRAND's
@@ -336,6 +371,7 @@ __device__ __forceinline__ void substep_vector(const SubstepArgs& a, uint32_t i,
 // ---- TAPE / PHILOX ------------------------------------------------------------
 template <int N, int kRng, bool kFirst, bool kNext, bool kMerge = false>
 __global__ void __launch_bounds__(kBlock) substep_kernel(const SubstepArgs a) {
+  pdl_prologue();
   const uint32_t v = blockIdx.x * kBlock + threadIdx.x;
   const uint32_t i = v * N;
   if (i >= a.g.total) return;
@@ -396,6 +432,7 @@ __device__ __forceinline__ void quad_transpose(float (&v)[4], uint32_t q) {
 
 template <bool kFirst, bool kNext>
 __global__ void __launch_bounds__(kBlock) substep_torchvec_kernel(const SubstepArgs a) {
+  pdl_prologue();
   const uint32_t T = a.torch_T;
   const uint32_t t = blockIdx.x * kBlock + threadIdx.x;  // torch thread == Philox subsequence (grid.x*256 == T)
   const uint32_t k = blockIdx.y;                          // index of the curand_normal4 call
@@ -425,6 +462,7 @@ __global__ void __launch_bounds__(kBlock) substep_torchvec_kernel(const SubstepA
 // elements and the stream matches the eager reference on the same generator.
 template <bool kFirst, bool kNext>
 __global__ void __launch_bounds__(kBlock) substep_torch_kernel(const SubstepArgs a) {
+  pdl_prologue();
   const uint32_t T = a.torch_T;
   const uint32_t tid = blockIdx.x * kBlock + threadIdx.x;
   if (tid >= T) return;
@@ -495,6 +533,7 @@ __device__ __forceinline__ float advance_element(float x, float c, bool known, f
 
 template <int kRng>
 __global__ void __launch_bounds__(kBlock) advance_kernel(const AdvanceArgs a) {
+  pdl_prologue();
   const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= a.g.total) return;
   uint32_t row, mi;
@@ -515,6 +554,7 @@ __global__ void __launch_bounds__(kBlock) advance_kernel(const AdvanceArgs a) {
 }
 
 __global__ void __launch_bounds__(kBlock) advance_torch_kernel(const AdvanceArgs a) {
+  pdl_prologue();
   const uint32_t T = a.torch_T;
   const uint32_t tid = blockIdx.x * kBlock + threadIdx.x;
   if (tid >= T) return;
@@ -560,6 +600,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 template <int N>
 __global__ void __launch_bounds__(kBlock) stop_stats_kernel(const StatsArgs s) {
+  pdl_prologue();
   float acc_in = 0.f, acc_ring = 0.f;
   const uint32_t stride = gridDim.x * kBlock * N;
   for (uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N; i < s.g.total; i += stride) {
@@ -613,6 +654,7 @@ __global__ void __launch_bounds__(kBlock) prologue_kernel(const float* x, const 
                                                           const uint8_t* __restrict__ mask, float* x_model,
                                                           float* x_copy, const float* __restrict__ table,
                                                           Geometry g) {
+  pdl_prologue();
   const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
   if (i >= g.total) return;
   uint32_t row, mi;
@@ -636,6 +678,7 @@ __global__ void __launch_bounds__(kBlock) epilogue_kernel(const float* __restric
                                                           const float* __restrict__ y,
                                                           const uint8_t* __restrict__ mask, float* out,
                                                           Geometry g) {
+  pdl_prologue();
   const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
   if (i >= g.total) return;
   uint32_t row, mi;
@@ -655,6 +698,7 @@ __global__ void __launch_bounds__(kBlock) epilogue_euler_kernel(const float* __r
                                                                 const float* __restrict__ y,
                                                                 const uint8_t* __restrict__ mask, float* x,
                                                                 float* out, float coef, Geometry g) {
+  pdl_prologue();
   const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
   if (i >= g.total) return;
   uint32_t row, mi;
@@ -680,6 +724,7 @@ __global__ void __launch_bounds__(kBlock) epilogue_cfg_kernel(const float* __res
                                                               const float* __restrict__ y,
                                                               const uint8_t* __restrict__ mask, float* x, float* out,
                                                               float coef, Geometry g) {
+  pdl_prologue();
   const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
   if (i >= g.total) return;
   uint32_t row, mi;
@@ -708,6 +753,7 @@ __global__ void __launch_bounds__(kBlock) step_boundary_kernel(const float* __re
                                                                const uint8_t* __restrict__ mask, float* x, float* out,
                                                                float coef, const float* __restrict__ next_table,
                                                                Geometry g) {
+  pdl_prologue();
   const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
   if (i >= g.total) return;
   uint32_t row, mi;
@@ -744,6 +790,7 @@ __global__ void __launch_bounds__(kBlock) step_boundary_kernel(const float* __re
 
 __global__ void __launch_bounds__(kBlock) pack_mask_kernel(const float* __restrict__ m, uint8_t* out,
                                                            uint32_t n, int invert) {
+  pdl_prologue();
   const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   const bool hi = __ldg(m + i) > 0.5f;
@@ -752,6 +799,7 @@ __global__ void __launch_bounds__(kBlock) pack_mask_kernel(const float* __restri
 
 __global__ void __launch_bounds__(kBlock) fill_normal_philox_kernel(float* out, uint32_t n, uint64_t seed,
                                                                     uint64_t draw, const uint64_t* st) {
+  pdl_prologue();
   const uint32_t i = blockIdx.x * kBlock + threadIdx.x;
   if (i >= n) return;
   if (st) {
@@ -764,6 +812,7 @@ __global__ void __launch_bounds__(kBlock) fill_normal_philox_kernel(float* out, 
 __global__ void __launch_bounds__(kBlock) fill_normal_torch_kernel(float* out, uint32_t n, uint64_t seed,
                                                                    uint64_t offset, const uint64_t* st,
                                                                    uint32_t T) {
+  pdl_prologue();
   const uint32_t tid = blockIdx.x * kBlock + threadIdx.x;
   if (tid >= T) return;
   if (st) {
@@ -785,6 +834,7 @@ template <int N>
 __global__ void __launch_bounds__(kBlock) synth_denoiser_kernel(const float* __restrict__ x, float* h0,
                                                                 float* h1, uint32_t n, float a0, float b0,
                                                                 float c0, float a1, float c1) {
+  pdl_prologue();
   const uint32_t i = (blockIdx.x * kBlock + threadIdx.x) * N;
   if (i >= n) return;
   float xv[N], u[N], w[N];
@@ -875,14 +925,14 @@ template <int N, int kRng>
 int launch_substep_vec(const SubstepArgs& a, bool first, bool next, bool merge, cudaStream_t s) {
   const unsigned grid = blocks_for((a.g.total + N - 1) / N);
   if (merge && kRng == LP_RNG_PHILOX) {
-    if (first) substep_kernel<N, LP_RNG_PHILOX, true, true, true><<<grid, kBlock, 0, s>>>(a);
-    else substep_kernel<N, LP_RNG_PHILOX, false, true, true><<<grid, kBlock, 0, s>>>(a);
+    if (first) launch_kernel(substep_kernel<N, LP_RNG_PHILOX, true, true, true>, dim3(grid), s, a);
+    else launch_kernel(substep_kernel<N, LP_RNG_PHILOX, false, true, true>, dim3(grid), s, a);
     return check_launch();
   }
-  if (first && next) substep_kernel<N, kRng, true, true><<<grid, kBlock, 0, s>>>(a);
-  else if (first) substep_kernel<N, kRng, true, false><<<grid, kBlock, 0, s>>>(a);
-  else if (next) substep_kernel<N, kRng, false, true><<<grid, kBlock, 0, s>>>(a);
-  else substep_kernel<N, kRng, false, false><<<grid, kBlock, 0, s>>>(a);
+  if (first && next) launch_kernel(substep_kernel<N, kRng, true, true>, dim3(grid), s, a);
+  else if (first) launch_kernel(substep_kernel<N, kRng, true, false>, dim3(grid), s, a);
+  else if (next) launch_kernel(substep_kernel<N, kRng, false, true>, dim3(grid), s, a);
+  else launch_kernel(substep_kernel<N, kRng, false, false>, dim3(grid), s, a);
   return check_launch();
 }
 
@@ -944,7 +994,7 @@ extern "C" int lp_pack_mask_f32(const float* mask_f32, uint8_t* mask_u8, int64_t
   if (!mask_f32 || !mask_u8 || n < 0) return LP_ERR_INVALID;
   if (n >= (int64_t(1) << 31)) return LP_ERR_UNSUPPORTED;
   if (n == 0) return LP_OK;
-  pack_mask_kernel<<<blocks_for((uint32_t)n), kBlock, 0, (cudaStream_t)stream>>>(mask_f32, mask_u8,
+  launch_kernel(pack_mask_kernel, dim3(blocks_for((uint32_t)n)), (cudaStream_t)stream, mask_f32, mask_u8,
                                                                                  (uint32_t)n, invert);
   return check_launch();
 }
@@ -959,8 +1009,8 @@ extern "C" int lp_prologue_f32(const float* x, const float* y, const float* nois
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 = geometry_vec4(g, mask) && aligned16(x) && aligned16(y) && aligned16(noise) &&
                   aligned16(x_model) && (!x_copy || aligned16(x_copy));
-  if (v4) prologue_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(x, y, noise, mask, x_model, x_copy, table, g);
-  else prologue_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(x, y, noise, mask, x_model, x_copy, table, g);
+  if (v4) launch_kernel(prologue_kernel<4>, dim3(blocks_for(g.total / 4)), s, x, y, noise, mask, x_model, x_copy, table, g);
+  else launch_kernel(prologue_kernel<1>, dim3(blocks_for(g.total)), s, x, y, noise, mask, x_model, x_copy, table, g);
   return check_launch();
 }
 
@@ -1000,16 +1050,16 @@ static int substep_impl(float* x_model, const float* x0, const float* x0_big, co
     const uint64_t calls = ((uint64_t)a.g.total + 4ull * a.torch_T - 1) / (4ull * a.torch_T);
     if (tv4 && calls <= 65535) {
       const dim3 g2(gb, (unsigned)calls);
-      if (f && n) substep_torchvec_kernel<true, true><<<g2, kBlock, 0, s>>>(a);
-      else if (f) substep_torchvec_kernel<true, false><<<g2, kBlock, 0, s>>>(a);
-      else if (n) substep_torchvec_kernel<false, true><<<g2, kBlock, 0, s>>>(a);
-      else substep_torchvec_kernel<false, false><<<g2, kBlock, 0, s>>>(a);
+      if (f && n) launch_kernel(substep_torchvec_kernel<true, true>, dim3(g2), s, a);
+      else if (f) launch_kernel(substep_torchvec_kernel<true, false>, dim3(g2), s, a);
+      else if (n) launch_kernel(substep_torchvec_kernel<false, true>, dim3(g2), s, a);
+      else launch_kernel(substep_torchvec_kernel<false, false>, dim3(g2), s, a);
       return check_launch();
     }
-    if (f && n) substep_torch_kernel<true, true><<<gb, kBlock, 0, s>>>(a);
-    else if (f) substep_torch_kernel<true, false><<<gb, kBlock, 0, s>>>(a);
-    else if (n) substep_torch_kernel<false, true><<<gb, kBlock, 0, s>>>(a);
-    else substep_torch_kernel<false, false><<<gb, kBlock, 0, s>>>(a);
+    if (f && n) launch_kernel(substep_torch_kernel<true, true>, dim3(gb), s, a);
+    else if (f) launch_kernel(substep_torch_kernel<true, false>, dim3(gb), s, a);
+    else if (n) launch_kernel(substep_torch_kernel<false, true>, dim3(gb), s, a);
+    else launch_kernel(substep_torch_kernel<false, false>, dim3(gb), s, a);
     return check_launch();
   }
 
@@ -1055,8 +1105,8 @@ extern "C" int lp_step_boundary_f32(const float* model_out, const float* y, cons
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 = geometry_vec4(g, mask) && aligned16(model_out) && aligned16(y) && aligned16(noise) &&
                   aligned16(x_inout) && aligned16(out);
-  if (v4) step_boundary_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(model_out, y, noise, mask, x_inout, out, euler_coef, next_table, g);
-  else step_boundary_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(model_out, y, noise, mask, x_inout, out, euler_coef, next_table, g);
+  if (v4) launch_kernel(step_boundary_kernel<4>, dim3(blocks_for(g.total / 4)), s, model_out, y, noise, mask, x_inout, out, euler_coef, next_table, g);
+  else launch_kernel(step_boundary_kernel<1>, dim3(blocks_for(g.total)), s, model_out, y, noise, mask, x_inout, out, euler_coef, next_table, g);
   return check_launch();
 }
 
@@ -1070,8 +1120,8 @@ extern "C" int lp_epilogue_cfg_f32(const float* cond, const float* uncond, float
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 = geometry_vec4(g, mask) && aligned16(cond) && aligned16(uncond) && aligned16(y) && aligned16(out) &&
                   (!x_inout || aligned16(x_inout));
-  if (v4) epilogue_cfg_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(cond, uncond, cfg, y, mask, x_inout, out, euler_coef, g);
-  else epilogue_cfg_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(cond, uncond, cfg, y, mask, x_inout, out, euler_coef, g);
+  if (v4) launch_kernel(epilogue_cfg_kernel<4>, dim3(blocks_for(g.total / 4)), s, cond, uncond, cfg, y, mask, x_inout, out, euler_coef, g);
+  else launch_kernel(epilogue_cfg_kernel<1>, dim3(blocks_for(g.total)), s, cond, uncond, cfg, y, mask, x_inout, out, euler_coef, g);
   return check_launch();
 }
 
@@ -1088,12 +1138,12 @@ extern "C" int lp_advance_f32(float* x_model, const float* c_state, const uint8_
     int64_t grid = 0;
     if (int rc = torch_grid(a.g.total, -1, &grid, nullptr)) return rc;
     a.torch_T = (uint32_t)(grid * 256);
-    advance_torch_kernel<<<(unsigned)grid, kBlock, 0, s>>>(a);
+    launch_kernel(advance_torch_kernel, dim3((unsigned)grid), s, a);
   } else if (rng->mode == LP_RNG_TAPE) {
     if (!rng->tape0) return LP_ERR_INVALID;
-    advance_kernel<LP_RNG_TAPE><<<blocks_for(a.g.total), kBlock, 0, s>>>(a);
+    launch_kernel(advance_kernel<LP_RNG_TAPE>, dim3(blocks_for(a.g.total)), s, a);
   } else if (rng->mode == LP_RNG_PHILOX) {
-    advance_kernel<LP_RNG_PHILOX><<<blocks_for(a.g.total), kBlock, 0, s>>>(a);
+    launch_kernel(advance_kernel<LP_RNG_PHILOX>, dim3(blocks_for(a.g.total)), s, a);
   } else {
     return LP_ERR_INVALID;
   }
@@ -1108,8 +1158,8 @@ extern "C" int lp_epilogue_f32(const float* model_out, const float* y, const uin
   if (g.total == 0) return LP_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 = geometry_vec4(g, mask) && aligned16(model_out) && aligned16(y) && aligned16(out);
-  if (v4) epilogue_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(model_out, y, mask, out, g);
-  else epilogue_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(model_out, y, mask, out, g);
+  if (v4) launch_kernel(epilogue_kernel<4>, dim3(blocks_for(g.total / 4)), s, model_out, y, mask, out, g);
+  else launch_kernel(epilogue_kernel<1>, dim3(blocks_for(g.total)), s, model_out, y, mask, out, g);
   return check_launch();
 }
 
@@ -1121,8 +1171,8 @@ extern "C" int lp_epilogue_euler_f32(const float* model_out, const float* y, con
   if (g.total == 0) return LP_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 = geometry_vec4(g, mask) && aligned16(model_out) && aligned16(y) && aligned16(out) && aligned16(x_inout);
-  if (v4) epilogue_euler_kernel<4><<<blocks_for(g.total / 4), kBlock, 0, s>>>(model_out, y, mask, x_inout, out, euler_coef, g);
-  else epilogue_euler_kernel<1><<<blocks_for(g.total), kBlock, 0, s>>>(model_out, y, mask, x_inout, out, euler_coef, g);
+  if (v4) launch_kernel(epilogue_euler_kernel<4>, dim3(blocks_for(g.total / 4)), s, model_out, y, mask, x_inout, out, euler_coef, g);
+  else launch_kernel(epilogue_euler_kernel<1>, dim3(blocks_for(g.total)), s, model_out, y, mask, x_inout, out, euler_coef, g);
   return check_launch();
 }
 
@@ -1143,8 +1193,8 @@ extern "C" int lp_stop_stats_f32(const float* a, const float* b, const uint8_t* 
   unsigned grid = blocks_for(groups);
   const unsigned cap = (unsigned)sms * 8;  // persistent-sized: 8 CTAs of 256 threads per SM
   if (grid > cap) grid = cap;
-  if (v4) stop_stats_kernel<4><<<grid, kBlock, 0, st>>>(s);
-  else stop_stats_kernel<1><<<grid, kBlock, 0, st>>>(s);
+  if (v4) launch_kernel(stop_stats_kernel<4>, dim3(grid), st, s);
+  else launch_kernel(stop_stats_kernel<1>, dim3(grid), st, s);
   return check_launch();
 }
 
@@ -1154,14 +1204,14 @@ extern "C" int lp_fill_normal_f32(float* out, int64_t n, const lp_rng* rng, lp_s
   if (n == 0) return LP_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (rng->mode == LP_RNG_PHILOX) {
-    fill_normal_philox_kernel<<<blocks_for((uint32_t)n), kBlock, 0, s>>>(out, (uint32_t)n, rng->seed,
+    launch_kernel(fill_normal_philox_kernel, dim3(blocks_for((uint32_t)n)), s, out, (uint32_t)n, rng->seed,
                                                                         rng->draw0, rng->state);
     return check_launch();
   }
   if (rng->mode == LP_RNG_TORCH) {
     int64_t grid = 0;
     if (int rc = torch_grid(n, -1, &grid, nullptr)) return rc;
-    fill_normal_torch_kernel<<<(unsigned)grid, kBlock, 0, s>>>(out, (uint32_t)n, rng->seed, rng->draw0,
+    launch_kernel(fill_normal_torch_kernel, dim3((unsigned)grid), s, out, (uint32_t)n, rng->seed, rng->draw0,
                                                               rng->state, (uint32_t)(grid * 256));
     return check_launch();
   }
@@ -1176,10 +1226,10 @@ extern "C" int lp_synth_denoiser_f32(const float* x, float* h0, float* h1, int64
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 = n % 4 == 0 && aligned16(x) && aligned16(h0) && (!h1 || aligned16(h1));
   if (v4)
-    synth_denoiser_kernel<4><<<blocks_for((uint32_t)n / 4), kBlock, 0, s>>>(x, h0, h1, (uint32_t)n, coef[0],
+    launch_kernel(synth_denoiser_kernel<4>, dim3(blocks_for((uint32_t)n / 4)), s, x, h0, h1, (uint32_t)n, coef[0],
                                                                           coef[1], coef[2], coef[3], coef[4]);
   else
-    synth_denoiser_kernel<1><<<blocks_for((uint32_t)n), kBlock, 0, s>>>(x, h0, h1, (uint32_t)n, coef[0], coef[1],
+    launch_kernel(synth_denoiser_kernel<1>, dim3(blocks_for((uint32_t)n)), s, x, h0, h1, (uint32_t)n, coef[0], coef[1],
                                                                       coef[2], coef[3], coef[4]);
   return check_launch();
 }
