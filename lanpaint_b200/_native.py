@@ -9,7 +9,8 @@ import ctypes as C
 import os
 from typing import Optional
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "liblanpaint_b200.so")
+_LIB_PATH = os.environ.get("LANPAINT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
+                                                               "liblanpaint_b200.so")
 
 ABI_VERSION = 3
 TABLE_STRIDE = 32

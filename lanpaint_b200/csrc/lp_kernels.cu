@@ -370,7 +370,7 @@ __device__ __forceinline__ void substep_vector(const SubstepArgs& a, uint32_t i,
 
 // ---- TAPE / PHILOX ------------------------------------------------------------
 template <int N, int kRng, bool kFirst, bool kNext, bool kMerge = false>
-__global__ void __launch_bounds__(kBlock) substep_kernel(const SubstepArgs a) {
+__global__ void __launch_bounds__(kBlock, 5) substep_kernel(const SubstepArgs a) {
   pdl_prologue();
   const uint32_t v = blockIdx.x * kBlock + threadIdx.x;
   const uint32_t i = v * N;
