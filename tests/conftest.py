@@ -15,6 +15,13 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    # keep the in-tree CUDA library in step with its sources (nvcc cross-compiles sm_100a without a GPU);
+    # if nvcc is unavailable the tests that need the library fail loudly on their own
+    try:
+        from lanpaint_b200 import build as _b
+        _b.build(force=False)
+    except Exception as e:  # pragma: no cover
+        print(f"[conftest] could not (re)build liblanpaint_b200.so: {e}")
 
 
 def golden_names():
