@@ -167,3 +167,45 @@ def test_nodes_run_under_inference_mode(cuda_device):
     with torch.inference_mode():
         inf = run()
     assert torch.equal(plain, inf.clone())
+
+
+def test_flux_type_model_runs_on_the_flow_schedule(cuda_device):
+    """ModelType.FLUX: rectified-flow change of variables, cfg_BIG forced to 1.0 (nodes.py:334-337), flow-form
+    noise_scaling and inverse_noise_scaling; checked against the oracle's restatement of the same run."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    dev = cuda_device
+    g = torch.Generator().manual_seed(4)
+    y = torch.randn(1, 16, 16, 16, generator=g)
+    noise_mask = (torch.rand(1, 1, 16, 16, generator=g) < 0.5).float()
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser, model_type=minicomfy.ModelType.FLUX,
+                                                         latent_channels=16), dev)
+    sig = torch.tensor([0.98, 0.9, 0.75, 0.6, 0.45, 0.3, 0.15, 0.0])
+    guider = minicomfy.CFGGuider(patcher)
+    guider.set_conds(0.3, -0.2)
+    guider.set_cfg(3.5)
+    fixed_noise = torch.randn(1, 16, 16, 16, generator=g)
+
+    class HostNoise:
+        seed = 3
+
+        def generate_noise(self, latent):
+            return fixed_noise
+
+    torch.manual_seed(9)
+    out, _ = N.LanPaint_SamplerCustomAdvanced().sample(HostNoise(), guider, minicomfy.ksampler("euler"), sig,
+                                                       {"samples": y, "noise_mask": noise_mask}, 4, 5.0, 0.2,
+                                                       "Prompt First")
+    eng = N.LAST_ENGINE["engine"]
+    assert eng.IS_FLUX and guider.cfg_BIG == 1.0
+
+    class FlowGuider(_OracleGuider):
+        def __init__(self):
+            super().__init__(0.3, -0.2, 3.5, 1.0)
+            self.model_sampling = O.FlowSampling()
+    model = FlowGuider()
+    torch.manual_seed(9)
+    want = O.euler_inpaint(model, y.to(dev), fixed_noise.to(dev), noise_mask.expand(1, 16, 16, 16).to(dev), sig.to(dev),
+                           O.Hyper(n_steps=4, lam=5.0, step_size=0.2, min_step_frac=1.0, flow=True), max_denoise=True)
+    assert eng.model_calls == model.calls
+    assert max_rel(out["samples"], want) <= 1e-4
