@@ -18,7 +18,6 @@ from typing import Any, Callable, Optional
 import torch
 
 from . import _native
-from .types import LangevinState
 
 _P = C.c_void_p
 

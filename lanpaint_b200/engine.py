@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import ctypes as C
 import weakref
-from typing import Callable, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 import torch

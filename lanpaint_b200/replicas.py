@@ -9,7 +9,7 @@ max-over-ranks reduction of its duration, and optionally collecting results on r
 from __future__ import annotations
 
 import os
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import Iterable, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist

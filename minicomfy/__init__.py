@@ -17,7 +17,7 @@ from __future__ import annotations
 import math
 import sys
 import types
-from typing import Callable, Optional
+from typing import Callable
 
 import torch
 

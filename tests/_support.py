@@ -1,5 +1,4 @@
 """Shared helpers for the parity tests (test infrastructure; may import oracle/)."""
-import numpy as np
 import torch
 
 from oracle import langevin_oracle as O

@@ -10,7 +10,6 @@ import torch
 
 from conftest import GOLDEN_DIR, load_golden
 from _support import make_model, max_rel
-from oracle import langevin_oracle as O
 
 pytestmark = pytest.mark.gpu
 AV_CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "aux_av_*.npz")))

@@ -1,7 +1,6 @@
 """GPU: inner-loop early stop (row a13) against traces and outputs recorded from the REFERENCE's
 LanPaintEarlyStopper driven through its own LanPaint.__call__ (tests/golden/make_golden.py --earlystop)."""
 import glob
-import json
 import os
 
 import numpy as np

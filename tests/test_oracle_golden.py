@@ -4,9 +4,6 @@ tape), (2) against the known answers the reference's own tests assert
 (tests/test_av_schedule.py, tests/test_min_step_frac.py, tests/test_sho_regression.py
 in the reference tree), (3) against the schedule facts SURVEY 8d derives from it.
 CPU only."""
-import math
-
-import numpy as np
 import pytest
 import torch
 
