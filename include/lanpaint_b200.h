@@ -115,6 +115,11 @@ typedef struct lp_rng {
 int lp_abi_version(void);
 const char* lp_status_string(int status);
 int lp_last_cuda_error(void); /* cudaError_t of the last failed launch on this thread */
+/* Process-wide switches (also read once from the environment: LANPAINT_B200_PDL, LANPAINT_B200_TMA):
+ *   "pdl" 1|0  programmatic dependent launch on every kernel (default 1)
+ *   "tma" 0|1  use the TMA-staged persistent variant of the steady fused sub-step when eligible (default 0) */
+int lp_set_option(const char* name, int value);
+
 /* Host-only self test of the index arithmetic the kernels rely on (the multiply-shift division that
  * replaces `/` and `%` by per_row and spatial): returns the number of (n, d) pairs, out of `samples`
  * pseudo-random ones plus every edge case, for which it disagrees with n / d.  0 = sound. */

@@ -31,12 +31,31 @@ __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
-inline bool pdl_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("LANPAINT_B200_PDL");
-    return !(e && e[0] == '0');
-  }();
-  return on;
+// process-wide switches, initialised from the environment, adjustable through lp_set_option()
+static int g_opt_pdl = [] {
+  const char* e = getenv("LANPAINT_B200_PDL");
+  return (e && e[0] == '0') ? 0 : 1;
+}();
+static int g_opt_tma = [] {
+  const char* e = getenv("LANPAINT_B200_TMA");
+  return e ? atoi(e) : 0;
+}();
+
+inline bool pdl_enabled() { return g_opt_pdl != 0; }
+
+template <typename... KArgs, typename... Args>
+inline void launch_kernel_smem(void (*kernel)(KArgs...), dim3 grid, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kBlock);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 template <typename... KArgs, typename... Args>
@@ -403,6 +422,154 @@ __global__ void __launch_bounds__(kBlock, 5) substep_kernel(const SubstepArgs a)
     }
   }
   substep_vector<N, kFirst, kNext, kMerge>(a, i, xi1, xi2);
+}
+
+// ---- PHILOX, TMA-staged persistent variant of the steady fused sub-step ---------------------------
+// Same arithmetic and the same Philox stream as substep_kernel (results are bit-identical); different data
+// movement: a persistent grid (2 CTAs per SM) walks tiles of kTile consecutive elements of one (row, channel),
+// one elected thread streams each tile's five operand slices + mask slice into shared memory with
+// cp.async.bulk (the TMA unit, completion counted on an mbarrier), kStages tiles ahead, and the 256 threads
+// consume them with LDS.128 and write x / C back with STG.128.  Registers hold no loads in flight, so
+// bytes-in-flight per SM is set by kStages * 42 KB instead of by occupancy.
+constexpr int kTile = 2048;
+constexpr int kStages = 2;
+
+struct __align__(128) TmaStage {
+  float x[kTile], x0[kTile], x0b[kTile], y[kTile], c[kTile];
+  uint8_t m[kTile];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra.uni DONE;\n"
+      "bra.uni LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct TileGeom {
+  uint32_t tiles_per_channel, n_tiles, channels;
+};
+
+template <bool kFirst, bool kMerge>
+__global__ void __launch_bounds__(kBlock, 2) substep_tma_kernel(const SubstepArgs a, const TileGeom tg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  TmaStage* stage = reinterpret_cast<TmaStage*>(smem_raw);
+  __shared__ __align__(8) uint64_t full[kStages];
+  pdl_prologue();
+  const uint32_t S = a.g.spatial.d;
+  const bool aliased = a.x0b == a.x0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  auto tile_origin = [&](uint32_t tile, uint32_t& e0, uint32_t& len, uint32_t& row, uint32_t& mi0) {
+    const uint32_t rc = tile / tg.tiles_per_channel;          // row * channels + channel
+    const uint32_t s0 = (tile - rc * tg.tiles_per_channel) * kTile;
+    len = S - s0 < (uint32_t)kTile ? S - s0 : (uint32_t)kTile;
+    e0 = rc * S + s0;
+    row = rc / tg.channels;
+    mi0 = row * a.g.mask_row_stride + (rc - row * tg.channels) * a.g.mask_channel_stride + s0;
+  };
+  auto issue = [&](uint32_t tile, int s) {  // one thread
+    uint32_t e0, len, row, mi0;
+    tile_origin(tile, e0, len, row, mi0);
+    const uint32_t fb = len * 4u;
+    const uint32_t total = fb * (3u + (aliased ? 0u : 1u) + (kFirst ? 0u : 1u)) + len;
+    mbar_expect_tx(&full[s], total);
+    TmaStage& t = stage[s];
+    tma_load_1d(t.x, a.x + e0, fb, &full[s]);
+    tma_load_1d(t.x0, a.x0 + e0, fb, &full[s]);
+    if (!aliased) tma_load_1d(t.x0b, a.x0b + e0, fb, &full[s]);
+    tma_load_1d(t.y, a.y + e0, fb, &full[s]);
+    if (!kFirst) tma_load_1d(t.c, a.c + e0, fb, &full[s]);
+    tma_load_1d(t.m, a.mask + mi0, len, &full[s]);
+  };
+
+  uint64_t seed = a.seed, d0 = a.draw0, d1 = a.draw1;
+  if (a.rng_state) {
+    seed = a.rng_state[0];
+    d0 += a.rng_state[1];
+    d1 += a.rng_state[1];
+  }
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      const uint32_t tile = blockIdx.x + (uint32_t)s * gridDim.x;
+      if (tile < tg.n_tiles) issue(tile, s);
+    }
+  }
+  uint32_t k = 0;
+  for (uint32_t tile = blockIdx.x; tile < tg.n_tiles; tile += gridDim.x, ++k) {
+    const int s = (int)(k % kStages);
+    mbar_wait(&full[s], (k / kStages) & 1u);
+    uint32_t e0, len, row, mi0;
+    tile_origin(tile, e0, len, row, mi0);
+    const TmaStage& t = stage[s];
+    RowCoef<kFirst, true> rc;
+    rc.load(a.table + (size_t)row * LP_TABLE_STRIDE);
+#pragma unroll
+    for (int pass = 0; pass < kTile / (4 * kBlock); ++pass) {
+      const uint32_t v = threadIdx.x + pass * kBlock;  // vector inside the tile
+      if (4 * v < len) {
+        const float4 xv = reinterpret_cast<const float4*>(t.x)[v];
+        float4 x0v = reinterpret_cast<const float4*>(t.x0)[v];
+        float4 x0bv = aliased ? x0v : reinterpret_cast<const float4*>(t.x0b)[v];
+        const float4 yv = reinterpret_cast<const float4*>(t.y)[v];
+        const float4 cv = kFirst ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(t.c)[v];
+        const uchar4 mv = reinterpret_cast<const uchar4*>(t.m)[v];
+        float x[4] = {xv.x, xv.y, xv.z, xv.w}, x0[4] = {x0v.x, x0v.y, x0v.z, x0v.w};
+        float x0b[4] = {x0bv.x, x0bv.y, x0bv.z, x0bv.w}, y[4] = {yv.x, yv.y, yv.z, yv.w};
+        float cp[4] = {cv.x, cv.y, cv.z, cv.w}, cn[4], te[4];
+        const bool known[4] = {mv.x != 0, mv.y != 0, mv.z != 0, mv.w != 0};
+        if (a.use_cfg) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float u = x0b[j], d = __fsub_rn(x0[j], u);
+            x0[j] = __fadd_rn(u, __fmul_rn(d, a.cfg));
+            x0b[j] = __fadd_rn(u, __fmul_rn(d, a.cfg_big));
+          }
+        }
+        const uint32_t i = e0 + 4 * v;
+        const float4 n1 = philox_normal4(seed, d0, i >> 2);
+        float4 n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!kMerge) n2 = philox_normal4(seed, d1, i >> 2);
+        const float xi1[4] = {n1.x, n1.y, n1.z, n1.w}, xi2[4] = {n2.x, n2.y, n2.z, n2.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          substep_element<kFirst, true, kMerge>(x[j], x0[j], x0b[j], y[j], cp[j], known[j], xi1[j], xi2[j], rc, cn[j],
+                                                te[j]);
+        *reinterpret_cast<float4*>(a.x + i) = make_float4(x[0], x[1], x[2], x[3]);
+        *reinterpret_cast<float4*>(a.c + i) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      }
+    }
+    __syncthreads();  // every thread is done reading stage s
+    const uint32_t next = tile + (uint32_t)kStages * gridDim.x;
+    if (threadIdx.x == 0 && next < tg.n_tiles) issue(next, s);
+  }
 }
 
 // ---- TORCH, 128-bit path --------------------------------------------------------
@@ -921,9 +1088,49 @@ int torch_grid(int64_t numel, int device, int64_t* grid, uint64_t* inc) {
   return LP_OK;
 }
 
+inline int tma_mode() { return g_opt_tma; }  // 0 = never, 1 = when eligible (see lp_set_option)
+
+// The TMA-staged variant needs 16-byte aligned slices: spatial a multiple of 16 (mask slices) and no
+// side outputs; only worth it when there are enough tiles to keep a persistent grid busy.
+template <bool kFirst, bool kMerge>
+int launch_substep_tma(const SubstepArgs& a, cudaStream_t s) {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const size_t smem = sizeof(TmaStage) * kStages;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(substep_tma_kernel<kFirst, kMerge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  TileGeom tg;
+  tg.channels = a.g.per_row.d / a.g.spatial.d;
+  tg.tiles_per_channel = (a.g.spatial.d + kTile - 1) / kTile;
+  tg.n_tiles = (a.g.total / a.g.spatial.d) * tg.tiles_per_channel;
+  unsigned grid = (unsigned)sms * 2u;
+  if (grid > tg.n_tiles) grid = tg.n_tiles;
+  launch_kernel_smem(substep_tma_kernel<kFirst, kMerge>, dim3(grid), smem, s, a, tg);
+  return check_launch();
+}
+
+inline bool tma_eligible(const SubstepArgs& a) {
+  return tma_mode() != 0 && a.g.spatial.d % 16 == 0 && a.g.mask_row_stride % 16 == 0 && a.g.mask_channel_stride % 16 == 0 &&
+         (reinterpret_cast<uintptr_t>(a.mask) & 15u) == 0 && a.g.row_split == 0 && !a.x_copy && !a.x0e &&
+         a.g.total >= (1u << 20);
+}
+
 template <int N, int kRng>
 int launch_substep_vec(const SubstepArgs& a, bool first, bool next, bool merge, cudaStream_t s) {
   const unsigned grid = blocks_for((a.g.total + N - 1) / N);
+  if (N == 4 && kRng == LP_RNG_PHILOX && next && tma_eligible(a)) {
+    if (first && merge) return launch_substep_tma<true, true>(a, s);
+    if (first) return launch_substep_tma<true, false>(a, s);
+    if (merge) return launch_substep_tma<false, true>(a, s);
+    return launch_substep_tma<false, false>(a, s);
+  }
   if (merge && kRng == LP_RNG_PHILOX) {
     if (first) launch_kernel(substep_kernel<N, LP_RNG_PHILOX, true, true, true>, dim3(grid), s, a);
     else launch_kernel(substep_kernel<N, LP_RNG_PHILOX, false, true, true>, dim3(grid), s, a);
@@ -957,6 +1164,14 @@ extern "C" const char* lp_status_string(int status) {
 }
 
 extern "C" int lp_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" int lp_set_option(const char* name, int value) {
+  if (!name) return LP_ERR_INVALID;
+  const auto eq = [&](const char* k) { int i = 0; while (k[i] && name[i] == k[i]) ++i; return !k[i] && !name[i]; };
+  if (eq("pdl")) { g_opt_pdl = value; return LP_OK; }
+  if (eq("tma")) { g_opt_tma = value; return LP_OK; }
+  return LP_ERR_INVALID;
+}
 
 extern "C" int64_t lp_selftest_index_math(int64_t samples) {
   int64_t bad = 0;

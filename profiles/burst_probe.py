@@ -19,8 +19,11 @@ ap.add_argument("--requests", type=int, default=128)
 ap.add_argument("--rng", default="philox")
 ap.add_argument("--no-merge", action="store_true")
 ap.add_argument("--mask", default="random", choices=["random", "blob"])
+ap.add_argument("--tma", type=int, default=0)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
+from lanpaint_b200 import _native  # noqa: E402
+_native.load().lp_set_option(b"tma", args.tma)
 shape = (args.requests, 4, 128, 128)
 g = torch.Generator().manual_seed(0)
 y = torch.randn(shape, generator=g).to(dev)

@@ -677,3 +677,29 @@ def test_graph_statics_follow_the_tensor_not_the_address(cuda_device):
     out2 = run(eng, y2)
     want = run(_engine(SynthDenoiser(VESampling()), dict(n_steps=3), rng="philox", batched_replace="per_sample"), y2)
     assert torch.equal(out2, want) and not torch.equal(out1, out2), f"stale operand (same address: {same_address})"
+
+
+def test_tma_staged_variant_is_bit_identical(cuda_device):
+    """lp_set_option("tma", 1): the persistent cp.async.bulk/mbarrier variant of the steady kernel must produce
+    exactly what the LDG variant does (same arithmetic, same Philox stream) -- including a ragged last tile."""
+    from lanpaint_b200 import _native
+    from lanpaint_b200.runner import SynthDenoiser, VESampling
+    lib = _native.load()
+    dev = cuda_device
+    res = {}
+    try:
+        for shape in ((24, 4, 128, 128), (2, 16, 21, 80, 48)):      # S = 16384 (8 tiles) and S = 80640 (39.4 tiles)
+            x, y, noise, m = synth_inputs(shape, seed=31, device=dev)
+            sig = torch.full((shape[0],), 1.7)
+            times = tuple(O.times_from_sigma(sig, False))
+            for tma in (0, 1):
+                assert lib.lp_set_option(b"tma", tma) == 0
+                torch.manual_seed(17)
+                eng = _engine(SynthDenoiser(VESampling()), dict(n_steps=4), rng="philox", batched_replace="per_sample")
+                xx = x.clone()
+                out = eng(xx, y, noise, sig, m, times, None, 0, n_steps=4)
+                res[(shape, tma)] = (out, xx)
+            assert torch.equal(res[(shape, 0)][0], res[(shape, 1)][0])
+            assert torch.equal(res[(shape, 0)][1], res[(shape, 1)][1])
+    finally:
+        lib.lp_set_option(b"tma", 0)
