@@ -108,22 +108,15 @@ def dist_env():
 # on the host cores.  The one place outside tests/ where oracle/ is executed.
 # ------------------------------------------------------------------------------------------
 def calibrate_threads(requests: int) -> int:
-    """The reference's eager path is ~90 small element-wise ops per sub-step; on a many-core host
-    more threads can be slower (fork/join per op).  Pick the fastest thread count for this tensor
-    size from a quick op-chain probe, so the CPU arm is the best the host can do, not a strawman."""
+    """The reference's eager path is ~90 small element-wise ops per sub-step; on a many-core host more
+    threads can be much slower (fork/join per op).  Time ONE outer step of the actual workload (5 sub-steps,
+    6 model calls) per candidate thread count and keep the fastest, so the CPU arm is the best this host can
+    do rather than a strawman."""
     cores = os.cpu_count() or 1
-    x = torch.randn((requests,) + SHAPE)
-    y = torch.randn_like(x)
     best, best_t = 1, float("inf")
-    cands = sorted({c for c in (1, 2, 4, 8, 16, 32, 64, cores) if c <= cores})
-    for c in cands:
-        torch.set_num_threads(c)
-        for rep in range(2):
-            t0 = time.perf_counter()
-            z = x
-            for _ in range(10):
-                z = torch.exp(-(z * y)) * x + (1 - y) * z
-            dt = time.perf_counter() - t0
+    for c in sorted({k for k in (2, 4, 8, 16, 32, 64, cores) if k <= cores}):
+        cpu_job(requests, 1, c)                 # warm this thread count
+        dt = min(cpu_job(requests, 1, c)[0] for _ in range(2))
         if dt < best_t:
             best, best_t = c, dt
     return best
