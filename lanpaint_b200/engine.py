@@ -304,6 +304,8 @@ class LanPaint:
         if not (isinstance(x, torch.Tensor) and x.is_cuda):
             raise RuntimeError("lanpaint_b200.LanPaint needs CUDA tensors: there is no CPU or eager fallback "
                                "(the reference engine is the CPU implementation)")
+        if x.numel() == 0:  # an empty batch: nothing to update, nothing to draw, no model call
+            return torch.empty_like(x)
         opts = {}
         if isinstance(model_options, dict):
             opts = model_options.get("lanpaint_b200", {}) or {}

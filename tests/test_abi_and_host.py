@@ -145,3 +145,24 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cc", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_oversized_and_malformed_geometry_is_refused_before_any_launch():
+    """>= 2^31 elements is outside the 32-bit index arithmetic: the ABI says so (LP_ERR_UNSUPPORTED) instead of
+    wrapping around; inconsistent dims are LP_ERR_INVALID.  Both are decided before any CUDA call."""
+    lib = _native.load()
+    P = C.c_void_p
+    fake = P(0x1000)  # never dereferenced: validation fails first
+    big = _native.Dims(1 << 20, 4096, 1024, 4096, 1024, 0)          # 2^32 elements
+    assert lib.lp_prologue_f32(fake, fake, fake, fake, fake, None, fake, C.byref(big), None) == 4
+    assert lib.lp_epilogue_f32(fake, fake, fake, fake, C.byref(big), None) == 4
+    r = _native.Rng(mode=_native.RNG_PHILOX)
+    assert lib.lp_substep_f32(fake, fake, fake, fake, fake, fake, None, None, fake, C.byref(big), C.byref(r), 3, None) == 4
+    bad = _native.Dims(2, 100, 30, 100, 0, 0)                        # per_row not a multiple of spatial
+    assert lib.lp_epilogue_f32(fake, fake, fake, fake, C.byref(bad), None) == 1
+    neg = _native.Dims(2, 64, 16, 64, 16, 80)                        # row_split beyond the row
+    assert lib.lp_epilogue_f32(fake, fake, fake, fake, C.byref(neg), None) == 1
+    empty = _native.Dims(0, 64, 16, 64, 16, 0)                       # empty batch: a no-op that succeeds
+    assert lib.lp_epilogue_f32(fake, fake, fake, fake, C.byref(empty), None) == 0
+    assert lib.lp_substep_f32(fake, fake, fake, fake, fake, fake, None, None, fake, C.byref(empty), C.byref(r), 9, None) == 1
+    assert lib.lp_set_option(b"no-such-option", 1) == 1

@@ -243,6 +243,16 @@ def test_philox_mode_reproducible_and_sane(cuda_device):
 # ----------------------------------------------------------------------------
 # 4. edge cases and error behaviour
 # ----------------------------------------------------------------------------
+def test_empty_batch_is_a_no_op(cuda_device):
+    dev = cuda_device
+    x = torch.empty(0, 4, 16, 16, device=dev)
+    model = make_model("two_heads", False)
+    eng = _engine(model, dict(n_steps=3))
+    e = torch.empty(0, device=dev)
+    out = eng(x, x, x, e, x, (e, e, e), {}, 0, n_steps=3)
+    assert out.shape == x.shape and model.calls == 0
+
+
 def test_cpu_tensor_is_rejected_loudly():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
