@@ -38,6 +38,12 @@ try:  # WAN22 exists only in recent ComfyUI builds
 except Exception:  # pragma: no cover
     WAN22 = None
 
+try:  # MiniMax-H3 schedule helpers: present only in ComfyUI builds that ship the model
+    from comfy.ldm.minimax.model import time_shift_sigma, time_shift_slope
+except Exception:
+    time_shift_sigma = None
+    time_shift_slope = None
+
 from .engine import CfgPair, LanPaint, _IdentityCache, pack_mask
 from .schedule import effective_inner_steps, min_step_frac_effective_steps, times_from_sigma  # noqa: F401
 
@@ -57,6 +63,23 @@ KSAMPLER_NAMES = ["euler", "euler_ancestral", "heun", "heunpp2", "dpm_2", "dpm_2
 # retired widgets old workflows still send; accepted and ignored (nodes.py:472-477,538-548)
 _RETIRED_ALL = ("LanPaint_Beta", "LanPaint_Friction", "LanPaint_EarlyStop", "LanPaint_InnerThreshold",
                 "LanPaint_InnerPatience", "LanPaint_MinStepFrac")
+
+
+def _detect_minimax_h3_audio(model_patcher, model_options, latent_shapes):
+    """A MiniMax-H3 AV pack is a nested (video, audio) latent whose diffusion model carries
+    sigma_shift_video / sigma_shift_audio (nodes.py:34-52).  Returns (latent_shapes, shift_v, shift_a) or None;
+    `transformer_options` may override the shifts."""
+    if latent_shapes is None or len(latent_shapes) < 2:
+        return None
+    diff_model = getattr(getattr(model_patcher, "model", None), "diffusion_model", None)
+    shift_v = getattr(diff_model, "sigma_shift_video", None)
+    shift_a = getattr(diff_model, "sigma_shift_audio", None)
+    if shift_v is None or shift_a is None:
+        return None
+    topts = model_options.get("transformer_options", {}) if isinstance(model_options, dict) else {}
+    shift_v = topts.get("minimax_h3_sigma_shift_video", shift_v)
+    shift_a = topts.get("minimax_h3_sigma_shift_audio", shift_a)
+    return (latent_shapes, float(shift_v), float(shift_a))
 
 
 def _hidden(names):
@@ -188,7 +211,9 @@ class CFGGuider_LanPaint:
         device = self.model_patcher.load_device
         if WAN22 is not None and isinstance(self.inner_model, WAN22):
             self.inner_model.extra_conds = super(WAN22, self.inner_model).extra_conds
-        self.minimax_h3_audio = None  # AV per-row schedule: not built
+        # MiniMax-H3 AV packs carry an audio stream on a shifted sigma schedule (nodes.py:188-191)
+        self.minimax_h3_audio = _detect_minimax_h3_audio(self.model_patcher, self.model_options,
+                                                         kwargs.get("latent_shapes", None))
         if denoise_mask is not None and tuple(denoise_mask.shape) != tuple(noise.shape):
             denoise_mask = prepare_mask(denoise_mask, noise.shape, device,
                                         self.model_options.get("video_inpainting", False))
@@ -257,8 +282,24 @@ class KSamplerX0Inpaint:
             n_eff = effective_inner_steps(self.PaintMethod.n_steps, self.sigmas_host, float(sigma_host.mean()),
                                           float((1.0 - times[1]).mean()), self.LanPaint_early_stop,
                                           getattr(self, "LanPaint_min_step_frac", 1.0))
+            audio = {}
+            if self.audio_indicator is not None and self.audio_shifts is not None and time_shift_sigma is not None:
+                # the audio rows run on sigma_audio = time_shift_sigma(sigma_video, shift_v, shift_a) and the
+                # flat-grid target overshoots them by sigma_v*slope/sigma_a (nodes.py:254-275)
+                shift_v, shift_a = self.audio_shifts
+                flow_v = times[2]
+                flow_a = time_shift_sigma(flow_v, shift_v, shift_a)
+                abt_a = (1 - flow_a) ** 2 / ((1 - flow_a) ** 2 + flow_a ** 2)
+                c = 1.0
+                ft = float(flow_v)
+                if ft > 1e-4 and time_shift_slope is not None:
+                    c = float(flow_a) / (ft * float(time_shift_slope(flow_v, shift_v, shift_a)))
+                audio = dict(current_times_audio=(flow_a / (1 - flow_a), abt_a, flow_a),
+                             audio_indicator=self.audio_indicator,
+                             audio_correction=(1.0 - self.audio_indicator) + c * self.audio_indicator)
             out = self.PaintMethod(x, self.latent_image, self.noise, sigma_host,
-                                   self._latent_mask(denoise_mask, x), times, model_options, seed, n_steps=n_eff)
+                                   self._latent_mask(denoise_mask, x), times, model_options, seed, n_steps=n_eff,
+                                   **audio)
         step = model_options.get("i", kwargs.get("i", 0))
         if step % 2 == 0:  # preview every other step (nodes.py:304-313)
             callback = model_options.get("callback", None)
@@ -286,6 +327,14 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
         patcher = model_wrap.model_patcher
         model_wrap.cfg_BIG = 1.0 if is_flux else patcher.LanPaint_cfg_BIG
         noise = base.model_sampling.noise_scaling(sigmas[0], noise, latent_image, self.max_denoise(model_wrap, sigmas))
+        layout = getattr(model_wrap, "minimax_h3_audio", None)
+        if layout is not None and time_shift_sigma is not None:  # mark the audio rows of the flat pack (nodes.py:340-349)
+            latent_shapes, shift_v, shift_a = layout
+            video_n = math.prod(latent_shapes[0][1:])
+            indicator = torch.zeros(noise.shape, dtype=torch.float32, device=noise.device)
+            indicator[..., video_n:] = 1.0
+            model_k.audio_indicator = indicator
+            model_k.audio_shifts = (shift_v, shift_a)
         model_options = extra_args.get("model_options", {}) or {}
         model_k.PaintMethod = LanPaint(
             model_k.inner_model, patcher.LanPaint_NumSteps, patcher.LanPaint_Friction, patcher.LanPaint_Lambda,

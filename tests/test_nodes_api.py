@@ -123,3 +123,28 @@ def test_reshape_mask_matches_reference_outputs(nodes_mod):
         got = nodes_mod.reshape_mask(torch.from_numpy(z["in_" + key]), oshape, video)
         assert tuple(got.shape) == tuple(oshape), key
         assert torch.equal(got.contiguous(), torch.from_numpy(z["out_" + key])), key
+
+
+# ---- MiniMax-H3 detection (reference tests/test_av_schedule.py:75-105) -----------------------------------
+class _FakeDiffusion:
+    sigma_shift_video = 12.0
+    sigma_shift_audio = 3.0
+
+
+def _patcher(with_shifts=True):
+    import types
+    model = types.SimpleNamespace(diffusion_model=_FakeDiffusion()) if with_shifts else object()
+    return types.SimpleNamespace(model=model)
+
+
+_TWO = [(1, 24, 37, 30, 54), (1, 32, 2, 207)]
+
+
+def test_minimax_detection(nodes_mod):
+    det = nodes_mod._detect_minimax_h3_audio
+    assert det(_patcher(), {}, [(1, 24, 37, 30, 54)]) is None and det(_patcher(), {}, None) is None
+    assert det(_patcher(False), {}, _TWO) is None
+    assert det(_patcher(), {}, _TWO) == (_TWO, 12.0, 3.0)
+    over = {"transformer_options": {"minimax_h3_sigma_shift_video": 10.0, "minimax_h3_sigma_shift_audio": 2.5}}
+    assert det(_patcher(), over, _TWO) == (_TWO, 10.0, 2.5)
+    assert nodes_mod.time_shift_sigma is None   # comfy.ldm.minimax is not importable in the stand-in
