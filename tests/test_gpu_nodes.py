@@ -209,3 +209,26 @@ def test_flux_type_model_runs_on_the_flow_schedule(cuda_device):
                            O.Hyper(n_steps=4, lam=5.0, step_size=0.2, min_step_frac=1.0, flow=True), max_denoise=True)
     assert eng.model_calls == model.calls
     assert max_rel(out["samples"], want) <= 1e-4
+
+
+def test_node_path_with_graph_replay_equals_eager(cuda_device):
+    """model_options["lanpaint_b200"] = {"cuda_graph": True}: the whole outer step, including the guider's
+    cond/uncond evaluations, is captured once per sub-step count and replayed; results must not change."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    dev = cuda_device
+    g = torch.Generator().manual_seed(6)
+    y = torch.randn(1, 4, 32, 32, generator=g)
+    noise_mask = (torch.rand(1, 1, 32, 32, generator=g) < 0.5).float()
+    res = {}
+    for graph in (False, True):
+        patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+        patcher.model_options["lanpaint_b200"] = {"cuda_graph": graph}
+        (out,) = N.LanPaint_KSampler().sample(patcher, 11, 20, 5.0, "euler", "karras", 0.3, -0.2,
+                                              {"samples": y, "noise_mask": noise_mask}, 1.0, 5, "Image First", "",
+                                              N.IMAGE_MODE)
+        res[graph] = (out["samples"], N.LAST_ENGINE["engine"])
+    assert torch.equal(res[True][0], res[False][0])
+    eng = res[True][1]
+    assert len([v for v in eng._graphs.values() if v]) == 6       # sub-step counts 5,4,3,2,1,0 of karras-20 x N=5
+    assert eng.model_calls == 73 and eng.substeps_done == 53
