@@ -7,7 +7,7 @@ Public surface
                       the ComfyUI custom-node protocol (reference: __init__.py:90-98,
                       src/LanPaint/nodes.py:1347-1378), resolved lazily because they need ComfyUI
 """
-from .types import LangevinState  # noqa: F401
+from .state import LangevinState  # noqa: F401
 
 __version__ = "0.1.0"
 WEB_DIRECTORY = "./web"

@@ -30,7 +30,7 @@ import torch
 
 from . import _native
 from .schedule import Hyper, build_table, mean_half_dt
-from .types import LangevinState
+from .state import LangevinState
 
 _P = C.c_void_p
 
@@ -659,9 +659,7 @@ class LanPaint:
         (src/LanPaint/lanpaint.py:192-293).  Because the callback sits between the two half-advances
         this cannot use the cross-model fusion: it runs lp_advance_f32 (first half), the callback, then
         lp_substep_f32 (Coef_C + correction + second half) -- 2 launches instead of ~89."""
-        if args is not None and not isinstance(args, LangevinState):
-            if isinstance(args, tuple):
-                args = LangevinState(args[0], args[1], args[2] if len(args) >= 3 else None)
+        args = LangevinState.coerce(args)
         if not (isinstance(x_t, torch.Tensor) and x_t.is_cuda):
             raise RuntimeError("lanpaint_b200.LanPaint.langevin_dynamics needs CUDA tensors")
         lib = _native.load()

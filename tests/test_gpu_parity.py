@@ -522,7 +522,7 @@ def test_langevin_dynamics_method_matches_oracle(cuda_device):
     """Same call as the reference's tests/test_sho_regression.py, checked numerically against the oracle's
     restatement of lanpaint.py:192-293 for a first and a steady sub-step with an arbitrary score callback."""
     from lanpaint_b200.engine import NoiseTape
-    from lanpaint_b200.types import LangevinState
+    from lanpaint_b200.state import LangevinState
     dev = cuda_device
     torch.manual_seed(0)
     shape = (2, 4, 16, 16)
