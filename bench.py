@@ -115,7 +115,9 @@ def calibrate_threads(requests: int) -> int:
     cores = os.cpu_count() or 1
     best, best_t = 1, float("inf")
     for c in sorted({k for k in (2, 4, 8, 16, 32, 64, cores) if k <= cores}):
-        cpu_job(requests, 1, c)                 # warm this thread count
+        warm = cpu_job(requests, 1, c)[0]      # also warms this thread count
+        if warm > 2.5 * best_t:                # past the knee: more threads only get slower on this host
+            break
         dt = min(cpu_job(requests, 1, c)[0] for _ in range(2))
         if dt < best_t:
             best, best_t = c, dt
