@@ -217,7 +217,8 @@ int lp_epilogue_f32(const float* model_out, const float* y, const uint8_t* mask,
  * (sample_euler: d = (x - denoised)/sigma; x = x + d*(sigma_next - sigma)), for hosts that own the
  * sampler loop:
  *   out = mask ? y : model_out ;  x = x + (x - out) * euler_coef      euler_coef = (sigma_next - sigma)/sigma
- * x_inout is the model-space state lp_substep_f32 left behind (the rewritten sampler x). */
+ * x_inout is the model-space state lp_substep_f32 left behind (the rewritten sampler x).  out may be NULL when
+ * nobody reads the denoised latent (no preview callback): the pass then writes only x. */
 int lp_epilogue_euler_f32(const float* model_out, const float* y, const uint8_t* mask, float* x_inout,
                           float* out, float euler_coef, const lp_dims* dims, lp_stream_t stream);
 
@@ -225,7 +226,7 @@ int lp_epilogue_euler_f32(const float* model_out, const float* y, const uint8_t*
  * (lanpaint.py:151-154), k-diffusion's Euler update, and the replace step of step s+1 (lanpaint.py:85-94,
  * coefficients rep_noise/rep_y of `next_table`):
  *   out = mask ? y : model_out ;  x = x + (x - out)*euler_coef ;  x = mask ? rep_n*noise + rep_y*y : x
- * Known positions never read x or model_out; free positions never read noise. */
+ * Known positions never read x or model_out; free positions never read noise.  out may be NULL. */
 int lp_step_boundary_f32(const float* model_out, const float* y, const float* noise, const uint8_t* mask,
                          float* x_inout, float* out, float euler_coef, const float* next_table,
                          const lp_dims* dims, lp_stream_t stream);

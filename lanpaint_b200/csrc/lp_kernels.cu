@@ -881,7 +881,7 @@ __global__ void __launch_bounds__(kBlock) epilogue_euler_kernel(const float* __r
     ov[j] = known[j] ? yv[j] : ov[j];
     xv[j] = fmaf(xv[j] - ov[j], coef, xv[j]);
   }
-  store_f<N>(out, i, ov);
+  if (out) store_f<N>(out, i, ov);
   store_f<N>(x, i, xv);
 }
 
@@ -951,7 +951,7 @@ __global__ void __launch_bounds__(kBlock) step_boundary_kernel(const float* __re
     ov[j] = o;
     xv[j] = known[j] ? fmaf(rn, nv[j], ry * yv[j]) : stepped;
   }
-  store_f<N>(out, i, ov);
+  if (out) store_f<N>(out, i, ov);
   store_f<N>(x, i, xv);
 }
 
@@ -1313,13 +1313,13 @@ extern "C" int lp_substep_cfg_f32(float* x_model, const float* cond, const float
 extern "C" int lp_step_boundary_f32(const float* model_out, const float* y, const float* noise, const uint8_t* mask,
                                     float* x_inout, float* out, float euler_coef, const float* next_table,
                                     const lp_dims* dims, lp_stream_t stream) {
-  if (!model_out || !y || !noise || !mask || !x_inout || !out || !next_table) return LP_ERR_INVALID;
+  if (!model_out || !y || !noise || !mask || !x_inout || !next_table) return LP_ERR_INVALID;
   Geometry g;
   if (int rc = make_geometry(dims, g)) return rc;
   if (g.total == 0) return LP_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const bool v4 = geometry_vec4(g, mask) && aligned16(model_out) && aligned16(y) && aligned16(noise) &&
-                  aligned16(x_inout) && aligned16(out);
+                  aligned16(x_inout) && (!out || aligned16(out));
   if (v4) launch_kernel(step_boundary_kernel<4>, dim3(blocks_for(g.total / 4)), s, model_out, y, noise, mask, x_inout, out, euler_coef, next_table, g);
   else launch_kernel(step_boundary_kernel<1>, dim3(blocks_for(g.total)), s, model_out, y, noise, mask, x_inout, out, euler_coef, next_table, g);
   return check_launch();
@@ -1380,12 +1380,13 @@ extern "C" int lp_epilogue_f32(const float* model_out, const float* y, const uin
 
 extern "C" int lp_epilogue_euler_f32(const float* model_out, const float* y, const uint8_t* mask, float* x_inout,
                                      float* out, float euler_coef, const lp_dims* dims, lp_stream_t stream) {
-  if (!model_out || !y || !mask || !x_inout || !out) return LP_ERR_INVALID;
+  if (!model_out || !y || !mask || !x_inout) return LP_ERR_INVALID;
   Geometry g;
   if (int rc = make_geometry(dims, g)) return rc;
   if (g.total == 0) return LP_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  const bool v4 = geometry_vec4(g, mask) && aligned16(model_out) && aligned16(y) && aligned16(out) && aligned16(x_inout);
+  const bool v4 = geometry_vec4(g, mask) && aligned16(model_out) && aligned16(y) && (!out || aligned16(out)) &&
+                  aligned16(x_inout);
   if (v4) launch_kernel(epilogue_euler_kernel<4>, dim3(blocks_for(g.total / 4)), s, model_out, y, mask, x_inout, out, euler_coef, g);
   else launch_kernel(epilogue_euler_kernel<1>, dim3(blocks_for(g.total)), s, model_out, y, mask, x_inout, out, euler_coef, g);
   return check_launch();

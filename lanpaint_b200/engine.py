@@ -518,7 +518,7 @@ class LanPaint:
         mo = _as_operand(mo, xm)
         if next_table is not None and euler_coef is not None:
             rc = lib.lp_step_boundary_f32(_P(mo.data_ptr()), _P(y.data_ptr()), _P(nz.data_ptr()),
-                                          _P(pm.data.data_ptr()), _P(xm.data_ptr()), _P(out.data_ptr()),
+                                          _P(pm.data.data_ptr()), _P(xm.data_ptr()), _P(_ptr(out)),
                                           C.c_float(euler_coef), _P(next_table.data_ptr()), C.byref(dims), stream)
             _native.check(rc, "lp_step_boundary_f32")
             self.launches += 1
@@ -528,7 +528,7 @@ class LanPaint:
                                      C.byref(dims), stream)
         else:  # host-owned sampler loop: fold k-diffusion's Euler update of x into the same pass
             rc = lib.lp_epilogue_euler_f32(_P(mo.data_ptr()), _P(y.data_ptr()), _P(pm.data.data_ptr()),
-                                           _P(xm.data_ptr()), _P(out.data_ptr()), C.c_float(euler_coef),
+                                           _P(xm.data_ptr()), _P(_ptr(out)), C.c_float(euler_coef),
                                            C.byref(dims), stream)
         _native.check(rc, "lp_epilogue_f32")
         self.launches += 1

@@ -254,10 +254,13 @@ class GraphedJob:
         for i, st in enumerate(self.sched.steps):
             coef = (st.sigma_next - st.sigma) / st.sigma
             last = i + 1 == len(self.sched.steps)
+            # the first replace step is a no-op when the replace form is noise_scaling's own form at sigmas[0]
+            # (every position of x already holds it); only the reference's batched flow-form quirk differs
+            first_is_noop = self.fused_euler and i == 0 and (self.shape[0] == 1 or eng.batched_replace == "per_sample")
             eng._launch_sequence(self.x, self.y, self.noise, pm, dims, self.tables[i], self.t_model[i], self.sigma[i],
-                                 self.c, self.out, self.active[i], plan, False, None, 0, None, state,
-                                 euler_coef=coef if self.fused_euler else None,
-                                 skip_prologue=self.fused_euler and i > 0,
+                                 self.c, None if self.fused_euler else self.out, self.active[i], plan, False, None, 0,
+                                 None, state, euler_coef=coef if self.fused_euler else None,
+                                 skip_prologue=(self.fused_euler and i > 0) or first_is_noop,
                                  next_table=self.tables[i + 1] if (self.fused_euler and not last) else None)
             if not self.fused_euler:
                 self.x.add_(self.x - self.out, alpha=coef)
