@@ -243,6 +243,28 @@ def langevin_substep(x_t: Tensor, score: Callable[[Tensor], Tensor], mask: Tenso
 
 
 # --------------------------------------------------------------------------
+# per-row schedule of one outer step (lanpaint.py:58-82)
+# --------------------------------------------------------------------------
+def per_row_schedule(sigma: Tensor, times: Times, hp: Hyper, audio: Optional[Audio], ndim: int):
+    """(VE, abt, flow_t, replace sigma, step size [lifted], times, correction).  With an AV pack the audio
+    positions take the audio stream's VE / abt and replace sigma (lanpaint.py:66-74); the step size is
+    StepSize * clamp(1 - abt, min=MinStepFrac) per position (lanpaint.py:81-82)."""
+    ve, abt, flow_t = times
+    rep_sigma = sigma
+    correction = None
+    if audio is not None:
+        ai = audio.indicator
+        ve = ve * (1 - ai) + audio.times.ve_sigma * ai
+        abt = abt * (1 - ai) + audio.times.abt * ai
+        rep_sigma = sigma * (1 - ai) + audio.times.flow_t * ai
+        times = Times(ve, abt, flow_t)
+        correction = audio.correction
+    step = hp.step_size * (1 - abt).clamp(min=hp.min_step_frac)
+    step = _lift(step, ndim)
+    return ve, abt, flow_t, rep_sigma, step, times, correction
+
+
+# --------------------------------------------------------------------------
 # one outer diffusion step (lanpaint.py:44-157)
 # --------------------------------------------------------------------------
 def outer_step(model, x: Tensor, y: Tensor, noise: Tensor, sigma: Tensor, mask: Tensor,
@@ -260,19 +282,7 @@ def outer_step(model, x: Tensor, y: Tensor, noise: Tensor, sigma: Tensor, mask: 
     if n_steps is None:
         n_steps = hp.n_steps
 
-    ve, abt, flow_t = times
-    rep_sigma = sigma
-    correction = None
-    if audio is not None:  # lanpaint.py:66-74
-        ai = audio.indicator
-        ve = ve * (1 - ai) + audio.times.ve_sigma * ai
-        abt = abt * (1 - ai) + audio.times.abt * ai
-        rep_sigma = sigma * (1 - ai) + audio.times.flow_t * ai
-        times = Times(ve, abt, flow_t)
-        correction = audio.correction
-
-    step = hp.step_size * (1 - abt).clamp(min=hp.min_step_frac)  # lanpaint.py:81
-    step = _lift(step, ndim)
+    ve, abt, flow_t, rep_sigma, step, times, correction = per_row_schedule(sigma, times, hp, audio, ndim)
 
     sampling = model.inner_model.model_sampling
     s = _lift(rep_sigma, ndim)

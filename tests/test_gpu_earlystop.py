@@ -85,3 +85,20 @@ def test_stats_kernel_matches_torch(cuda_device):
             assert abs(sums[1].item() / (d2 * ring.expand(shape).double()).sum().item() - 1) < 1e-5
         else:
             assert sums[1].item() == 0.0
+
+
+def test_early_stop_disabled_without_an_inpaint_region(cuda_device):
+    """reference tests/test_lanpaint_semantic_stop.py:68-104: with nothing to inpaint the stopper is never
+    built and all n sub-steps run; with a region and an easy threshold it stops after patience + 1 checks."""
+    from lanpaint_b200.engine import LanPaint
+    dev = cuda_device
+    x = torch.zeros(1, 4, 8, 8, device=dev)
+    y, noise = torch.zeros_like(x), torch.ones_like(x)
+    sig = torch.tensor([1.0], device=dev)
+    times = (sig, torch.tensor([0.5], device=dev), torch.tensor([0.0], device=dev))
+    for mask, patience, want_calls in ((torch.ones_like(x), 1, 10 + 1), (torch.zeros_like(x), 2, 3 + 1)):
+        model = make_model("identity", False)
+        eng = LanPaint(model, NSteps=10, Friction=15.0, Lambda=1.0, Beta=1.0, StepSize=0.2, rng="philox")
+        mo = {"lanpaint_semantic_stop": {"threshold": 1e6, "patience": patience}}
+        eng(x.clone(), y, noise, sig, mask, times, mo, 0, n_steps=10)
+        assert model.calls == want_calls, (model.calls, want_calls)

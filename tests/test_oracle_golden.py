@@ -64,6 +64,20 @@ def _flat_pack():
     return x, torch.zeros_like(x), torch.ones_like(x), torch.tensor([0.5]), video, audio, ai
 
 
+def test_audio_rows_get_audio_schedule_parameters():
+    """reference tests/test_av_schedule.py:157-199 -> abt 0.5 / 0.9 and step 0.2*(1-abt) per row with the engine's
+    default MinStepFrac = 0; without audio context the video schedule applies everywhere."""
+    x, y, noise, sigma, video, audio, ai = _flat_pack()
+    hp = O.Hyper(n_steps=1, lam=1.0, min_step_frac=0.0)
+    _, abt, _, rep, step, _, _ = O.per_row_schedule(sigma, video, hp, O.Audio(ai, audio, None), 3)
+    abt, step, rep = abt.flatten(), step.flatten(), rep.flatten()
+    assert abt[0] == 0.5 and abt[-1] == pytest.approx(0.9)
+    assert step[0] == pytest.approx(0.2 * 0.5) and step[-1] == pytest.approx(0.2 * (1 - 0.9))
+    assert rep[0] == pytest.approx(0.5) and rep[-1] == pytest.approx(0.2)
+    _, abt2, _, _, step2, _, _ = O.per_row_schedule(sigma, video, hp, None, 3)
+    assert abt2.flatten()[0] == 0.5 and abt2.numel() == 1 and step2.flatten()[0] == pytest.approx(0.1)
+
+
 def test_replace_step_uses_audio_sigma_on_audio_rows():
     """reference tests/test_av_schedule.py:204-219 -> 0.5 on video rows, 0.2 on audio rows."""
     x, y, noise, sigma, video, audio, ai = _flat_pack()
