@@ -96,6 +96,28 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off, so
+    eight ranks do not push their H2D/D2H traffic through one socket.  Returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -234,6 +256,7 @@ def run_b200(args):
     assert torch.cuda.is_available(), "bench.py (impl b200) needs a CUDA device; there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -392,6 +415,7 @@ def run_b200(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * R * sched.substeps * k2 / float(tt.item()), "unit": "sub-steps/s",
                "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "steps": k2, "in_flight": len(lanes),
+               "numa_node_rank0": numa,
                "api": ("lanpaint_b200.runner.GraphedJob.run" if gjob is not None else "lanpaint_b200.runner.euler_inpaint")
                       + "(engine=lanpaint_b200.LanPaint) on pinned host tensors, result to pinned host memory"}
 
