@@ -2,7 +2,7 @@
 
 Public surface
   LanPaint            the engine seam (reference: src/LanPaint/lanpaint.py)
-  LangevinState       reference: src/LanPaint/types.py
+  LangevinState       reference: src/LanPaint/types.py  (here: lanpaint_b200/state.py)
   NODE_CLASS_MAPPINGS / NODE_DISPLAY_NAME_MAPPINGS / WEB_DIRECTORY
                       the ComfyUI custom-node protocol (reference: __init__.py:90-98,
                       src/LanPaint/nodes.py:1347-1378), resolved lazily because they need ComfyUI

@@ -713,3 +713,44 @@ def test_tma_staged_variant_is_bit_identical(cuda_device):
             assert torch.equal(res[(shape, 0)][1], res[(shape, 1)][1])
     finally:
         lib.lp_set_option(b"tma", 0)
+
+
+# ----------------------------------------------------------------------------
+# 9. size-independent property at BASELINE size: the fused update is affine in its operands
+# ----------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [1 | 2, 2, 0])      # first+fused next, steady, last
+def test_update_is_affine_in_its_operands_at_full_size(flags, cuda_device):
+    """For fixed mask and coefficients, one launch maps (x, x0, x0_BIG, y, C, xi1, xi2) affinely to (x', C'):
+    f(u+v) - f(u) - f(v) + f(0) == 0.  Checked on [32,4,128,128] (BASELINE config 3) through the C ABI."""
+    from lanpaint_b200 import _native
+    from lanpaint_b200.schedule import Hyper, build_table
+    lib = _native.load()
+    dev = cuda_device
+    B, Cc, S = 32, 4, 128 * 128
+    shape = (B, Cc, S)
+    sig = torch.linspace(0.05, 14.0, B)
+    ve, abt, _ = O.times_from_sigma(sig, False)
+    tab = torch.from_numpy(build_table(abt.numpy(), ve.numpy(), Hyper(0.2, 5.0, 1.0, 1.0, False))).to(dev)
+    m8 = (torch.rand(B, 1, S, device=dev) < 0.5).to(torch.uint8)
+    dims = _native.Dims(B, Cc * S, S, S, 0, 0)
+    P = C.c_void_p
+    gen = torch.Generator(device=dev).manual_seed(0)
+    u = [torch.randn(shape, device=dev, generator=gen) for _ in range(7)]
+    v = [torch.randn(shape, device=dev, generator=gen) for _ in range(7)]
+
+    def f(ops):
+        x, x0, x0b, y, c, t0, t1 = (t.clone() for t in ops)
+        r = _native.Rng(mode=_native.RNG_TAPE, tape0=t0.data_ptr(), tape1=t1.data_ptr())
+        rc = lib.lp_substep_f32(P(x.data_ptr()), P(x0.data_ptr()), P(x0b.data_ptr()), P(y.data_ptr()), P(m8.data_ptr()),
+                                P(c.data_ptr()), None, None, P(tab.data_ptr()), C.byref(dims), C.byref(r),
+                                flags | 4, P(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        return x.double(), c.double()
+
+    zero = [torch.zeros(shape, device=dev) for _ in range(7)]
+    fu, fv, fuv, f0 = f(u), f(v), f([a + b for a, b in zip(u, v)]), f(zero)
+    for k in range(2):
+        resid = (fuv[k] - fu[k] - fv[k] + f0[k]).abs().max().item()
+        scale = max(fuv[k].abs().max().item(), 1.0)
+        assert resid <= 2e-5 * scale, (k, resid, scale)
+    assert f0[0].abs().max().item() == 0.0 and f0[1].abs().max().item() == 0.0   # and linear: f(0) = 0
