@@ -137,45 +137,50 @@ def euler_inpaint(engine, latent_image: torch.Tensor, noise: torch.Tensor, mask,
 
 
 def time_steady_substep(engine, latent_image: torch.Tensor, mask, sigma: float, launches: int = 53,
-                        repeats: int = 20, flow: bool = False):
+                        repeats: int = 20, flow: bool = False, rotate: int = 3):
     """Roofline probe: `launches` steady fused sub-step launches (flags = FUSE_NEXT, the kernel that
     dominates a job) back to back on job-shaped operands, between two CUDA events on the launching
     stream, `repeats` times.  Returns the list of per-launch durations in microseconds (one per repeat).
 
-    The operands are the real ones of a job (same shapes, mask, coefficient table, RNG mode); the
-    launches are identical to those `LanPaint._launch_sequence` issues, minus the model call between them."""
-    import ctypes as C
+    `rotate` independent operand sets (x, x0, x0_BIG, y, C, mask) are cycled, so a launch's operands were
+    last touched `rotate - 1` launches ago: with 176 MB per set at the bench's default size that is far more
+    than the 126 MB L2 can hold, i.e. every launch really streams from HBM (rotate=1 re-uses one set and lets
+    the L2 keep part of it -- reported separately as the L2-assisted figure).  The launches are identical to
+    those `LanPaint._launch_sequence` issues, minus the model call between them."""
     import numpy as np
     from .engine import PackedMask, _DrawPlan, pack_mask
     from .schedule import Hyper, build_table
     lib = _native.load()
     dev = latent_image.device
     B = latent_image.shape[0]
-    x = torch.randn_like(latent_image)
-    heads = engine.inner_model(x, torch.full((B,), sigma, device=dev))
-    x0, x0b = engine.unpack_model_output(heads)
-    x0, x0b = x0.clone(), x0b.clone()
-    cbuf = torch.randn_like(x)
-    pm = mask if isinstance(mask, PackedMask) else pack_mask(mask, x)
+    pm0 = mask if isinstance(mask, PackedMask) else pack_mask(mask, latent_image)
+    sets = []
+    for r in range(max(1, rotate)):
+        x = torch.randn_like(latent_image)
+        heads = engine.inner_model(x, torch.full((B,), sigma, device=dev))
+        x0, x0b = engine.unpack_model_output(heads)
+        sets.append(dict(x=x, x0=x0.clone(), x0b=x0b.clone(), y=latent_image if r == 0 else latent_image.clone(),
+                         c=torch.randn_like(x), m=pm0.data if r == 0 else pm0.data.clone()))
     s = torch.full((B,), sigma, dtype=torch.float32)
     ve, abt, _ = times_from_sigma(s, flow)
     hp = Hyper(engine.step_size, engine.chara_lamb, engine.chara_beta, engine.min_step_frac, flow)
     tab = torch.from_numpy(build_table(abt.numpy(), ve.numpy(), hp)).to(dev)
-    per_row = x.numel() // B
-    spatial = int(np.prod(x.shape[2:]))
-    dims = _native.Dims(B, per_row, spatial, pm.row_stride, pm.channel_stride)
-    plan = _DrawPlan(engine.rng, x, launches + 1)
+    per_row = latent_image.numel() // B
+    spatial = int(np.prod(latent_image.shape[2:]))
+    dims = _native.Dims(B, per_row, spatial, pm0.row_stride, pm0.channel_stride)
+    plan = _DrawPlan(engine.rng, latent_image, launches + 1)
     merge = plan.mode == _native.RNG_PHILOX and engine.merge_noise
     flags = _native.SUBSTEP_FUSE_NEXT | (_native.SUBSTEP_MERGE_NOISE if merge else 0)
     P = C.c_void_p
     stream = P(torch.cuda.current_stream(dev).cuda_stream)
 
     def burst():
-        for _ in range(launches):
+        for k in range(launches):
+            o = sets[k % len(sets)]
             r = plan.rng_struct(1 if merge else 2)
-            rc = lib.lp_substep_f32(P(x.data_ptr()), P(x0.data_ptr()), P(x0b.data_ptr()), P(latent_image.data_ptr()),
-                                    P(pm.data.data_ptr()), P(cbuf.data_ptr()), None, None, P(tab.data_ptr()),
-                                    C.byref(dims), C.byref(r), flags, stream)
+            rc = lib.lp_substep_f32(P(o["x"].data_ptr()), P(o["x0"].data_ptr()), P(o["x0b"].data_ptr()),
+                                    P(o["y"].data_ptr()), P(o["m"].data_ptr()), P(o["c"].data_ptr()), None, None,
+                                    P(tab.data_ptr()), C.byref(dims), C.byref(r), flags, stream)
             _native.check(rc, "lp_substep_f32")
 
     for _ in range(3):

@@ -20,6 +20,7 @@ ap.add_argument("--rng", default="philox")
 ap.add_argument("--no-merge", action="store_true")
 ap.add_argument("--mask", default="random", choices=["random", "blob"])
 ap.add_argument("--tma", type=int, default=0)
+ap.add_argument("--rotate", type=int, default=3, help="independent operand sets cycled (1 = L2-assisted)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 from lanpaint_b200 import _native  # noqa: E402
@@ -35,5 +36,5 @@ else:
     mask = (torch.rand((args.requests, 1, 128, 128), generator=g) < 0.5).float().to(dev)
 eng = LanPaint(SynthDenoiser(VESampling()), 5, 15.0, 5.0, 1.0, 0.2, MinStepFrac=1.0, rng=args.rng,
                merge_noise=not args.no_merge)
-ts = time_steady_substep(eng, y, pack_mask(mask, y), sigma=2.0, launches=53, repeats=5)
+ts = time_steady_substep(eng, y, pack_mask(mask, y), sigma=2.0, launches=53, repeats=5, rotate=args.rotate)
 print("per-launch us:", [round(t, 2) for t in ts])
