@@ -322,8 +322,10 @@ def run_b200(args):
     n_el = R * SHAPE[0] * SHAPE[1] * SHAPE[2]
     algo = ALGO_BYTES_PER_ELEM * n_el
     roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-            "kernel": "lp::substep_kernel<VEC=4, philox, first=0, fuse_next=1, merge=%d> (steady fused sub-step)"
-                      % (1 if args.rng == "philox" else 0), "peak_source": peak_src,
+            "kernel": ("lp::substep_tma_kernel<first=0, merge=1> (steady fused sub-step, TMA-staged persistent)"
+                       if args.rng == "philox" and n_el >= (1 << 20) else
+                       "lp::substep_kernel<VEC=4, %s, first=0, fuse_next=1> (steady fused sub-step)" % args.rng),
+            "peak_source": peak_src,
             "algorithmic_bytes_per_launch": algo}
     if args.kernel_timer:
         from lanpaint_b200.runner import time_steady_substep

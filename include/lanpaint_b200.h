@@ -117,7 +117,8 @@ const char* lp_status_string(int status);
 int lp_last_cuda_error(void); /* cudaError_t of the last failed launch on this thread */
 /* Process-wide switches (also read once from the environment: LANPAINT_B200_PDL, LANPAINT_B200_TMA):
  *   "pdl" 1|0  programmatic dependent launch on every kernel (default 1)
- *   "tma" 0|1  use the TMA-staged persistent variant of the steady fused sub-step when eligible (default 0) */
+ *   "tma" 1|0  use the TMA-staged persistent variant of the fused sub-step (cp.async.bulk + mbarrier ring) when
+ *              eligible: philox stream, >= 2^20 elements, spatial a multiple of 16 (default 1) */
 int lp_set_option(const char* name, int value);
 
 /* Host-only self test of the index arithmetic the kernels rely on (the multiply-shift division that

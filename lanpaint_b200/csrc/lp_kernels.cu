@@ -38,7 +38,7 @@ static int g_opt_pdl = [] {
 }();
 static int g_opt_tma = [] {
   const char* e = getenv("LANPAINT_B200_TMA");
-  return e ? atoi(e) : 0;
+  return e ? atoi(e) : 1;
 }();
 
 inline bool pdl_enabled() { return g_opt_pdl != 0; }
@@ -1088,7 +1088,7 @@ int torch_grid(int64_t numel, int device, int64_t* grid, uint64_t* inc) {
   return LP_OK;
 }
 
-inline int tma_mode() { return g_opt_tma; }  // 0 = never, 1 = when eligible (see lp_set_option)
+inline int tma_mode() { return g_opt_tma; }  // 1 (default) = when eligible, 0 = never (see lp_set_option)
 
 // The TMA-staged variant needs 16-byte aligned slices: spatial a multiple of 16 (mask slices) and no
 // side outputs; only worth it when there are enough tiles to keep a persistent grid busy.

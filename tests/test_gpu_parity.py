@@ -712,7 +712,7 @@ def test_tma_staged_variant_is_bit_identical(cuda_device):
             assert torch.equal(res[(shape, 0)][0], res[(shape, 1)][0])
             assert torch.equal(res[(shape, 0)][1], res[(shape, 1)][1])
     finally:
-        lib.lp_set_option(b"tma", 0)
+        lib.lp_set_option(b"tma", 1)   # the default
 
 
 # ----------------------------------------------------------------------------
