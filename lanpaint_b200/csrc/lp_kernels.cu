@@ -431,9 +431,7 @@ __global__ void __launch_bounds__(kBlock, 5) substep_kernel(const SubstepArgs a)
 // cp.async.bulk (the TMA unit, completion counted on an mbarrier), kStages tiles ahead, and the 256 threads
 // consume them with LDS.128 and write x / C back with STG.128.  Registers hold no loads in flight, so
 // bytes-in-flight per SM is set by kStages * 42 KB instead of by occupancy.
-constexpr int kTile = 2048;
-constexpr int kStages = 2;
-
+template <int kTile>
 struct __align__(128) TmaStage {
   float x[kTile], x0[kTile], x0b[kTile], y[kTile], c[kTile];
   uint8_t m[kTile];
@@ -471,10 +469,11 @@ struct TileGeom {
   uint32_t tiles_per_channel, n_tiles, channels;
 };
 
-template <bool kFirst, bool kMerge>
-__global__ void __launch_bounds__(kBlock, 2) substep_tma_kernel(const SubstepArgs a, const TileGeom tg) {
+template <bool kFirst, bool kMerge, int kTile, int kStages, int kMinBlocks>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) substep_tma_kernel(const SubstepArgs a, const TileGeom tg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  TmaStage* stage = reinterpret_cast<TmaStage*>(smem_raw);
+  using Stage = TmaStage<kTile>;
+  Stage* stage = reinterpret_cast<Stage*>(smem_raw);
   __shared__ __align__(8) uint64_t full[kStages];
   pdl_prologue();
   const uint32_t S = a.g.spatial.d;
@@ -500,7 +499,7 @@ __global__ void __launch_bounds__(kBlock, 2) substep_tma_kernel(const SubstepArg
     const uint32_t fb = len * 4u;
     const uint32_t total = fb * (3u + (aliased ? 0u : 1u) + (kFirst ? 0u : 1u)) + len;
     mbar_expect_tx(&full[s], total);
-    TmaStage& t = stage[s];
+    Stage& t = stage[s];
     tma_load_1d(t.x, a.x + e0, fb, &full[s]);
     tma_load_1d(t.x0, a.x0 + e0, fb, &full[s]);
     if (!aliased) tma_load_1d(t.x0b, a.x0b + e0, fb, &full[s]);
@@ -528,7 +527,7 @@ __global__ void __launch_bounds__(kBlock, 2) substep_tma_kernel(const SubstepArg
     mbar_wait(&full[s], (k / kStages) & 1u);
     uint32_t e0, len, row, mi0;
     tile_origin(tile, e0, len, row, mi0);
-    const TmaStage& t = stage[s];
+    const Stage& t = stage[s];
     RowCoef<kFirst, true> rc;
     rc.load(a.table + (size_t)row * LP_TABLE_STRIDE);
 #pragma unroll
@@ -1092,28 +1091,42 @@ inline int tma_mode() { return g_opt_tma; }  // 1 (default) = when eligible, 0 =
 
 // The TMA-staged variant needs 16-byte aligned slices: spatial a multiple of 16 (mask slices) and no
 // side outputs; only worth it when there are enough tiles to keep a persistent grid busy.
-template <bool kFirst, bool kMerge>
-int launch_substep_tma(const SubstepArgs& a, cudaStream_t s) {
+template <bool kFirst, bool kMerge, int kTile, int kStages, int kMinBlocks>
+int launch_substep_tma_cfg(const SubstepArgs& a, cudaStream_t s) {
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const size_t smem = sizeof(TmaStage) * kStages;
+  const size_t smem = sizeof(TmaStage<kTile>) * kStages;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(substep_tma_kernel<kFirst, kMerge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(substep_tma_kernel<kFirst, kMerge, kTile, kStages, kMinBlocks>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
   TileGeom tg;
   tg.channels = a.g.per_row.d / a.g.spatial.d;
   tg.tiles_per_channel = (a.g.spatial.d + kTile - 1) / kTile;
   tg.n_tiles = (a.g.total / a.g.spatial.d) * tg.tiles_per_channel;
-  unsigned grid = (unsigned)sms * 2u;
+  unsigned grid = (unsigned)sms * (unsigned)kMinBlocks;
   if (grid > tg.n_tiles) grid = tg.n_tiles;
-  launch_kernel_smem(substep_tma_kernel<kFirst, kMerge>, dim3(grid), smem, s, a, tg);
+  launch_kernel_smem(substep_tma_kernel<kFirst, kMerge, kTile, kStages, kMinBlocks>, dim3(grid), smem, s, a, tg);
   return check_launch();
+}
+
+// tile / ring geometry: "tma" option value 1 (default) = 2048-element tiles, 2 stages, 2 CTAs per SM;
+// 2, 3, 4 are the alternatives measured in profiles/README.md
+template <bool kFirst, bool kMerge>
+int launch_substep_tma(const SubstepArgs& a, cudaStream_t s) {
+  switch (tma_mode()) {
+    case 2: return launch_substep_tma_cfg<kFirst, kMerge, 1024, 4, 2>(a, s);
+    case 3: return launch_substep_tma_cfg<kFirst, kMerge, 4096, 2, 1>(a, s);
+    case 4: return launch_substep_tma_cfg<kFirst, kMerge, 2048, 4, 1>(a, s);
+    case 5: return launch_substep_tma_cfg<kFirst, kMerge, 1024, 3, 3>(a, s);
+    default: return launch_substep_tma_cfg<kFirst, kMerge, 2048, 2, 2>(a, s);
+  }
 }
 
 inline bool tma_eligible(const SubstepArgs& a) {
