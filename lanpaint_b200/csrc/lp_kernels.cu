@@ -469,7 +469,7 @@ struct TileGeom {
   uint32_t tiles_per_channel, n_tiles, channels;
 };
 
-template <bool kFirst, bool kMerge, int kTile, int kStages, int kMinBlocks>
+template <bool kFirst, bool kNext, bool kMerge, int kTile, int kStages, int kMinBlocks>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) substep_tma_kernel(const SubstepArgs a, const TileGeom tg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using Stage = TmaStage<kTile>;
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) substep_tma_kernel(const S
     uint32_t e0, len, row, mi0;
     tile_origin(tile, e0, len, row, mi0);
     const Stage& t = stage[s];
-    RowCoef<kFirst, true> rc;
+    RowCoef<kFirst, kNext> rc;
     rc.load(a.table + (size_t)row * LP_TABLE_STRIDE);
 #pragma unroll
     for (int pass = 0; pass < kTile / (4 * kBlock); ++pass) {
@@ -555,14 +555,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) substep_tma_kernel(const S
         const uint32_t i = e0 + 4 * v;
         const float4 n1 = philox_normal4(seed, d0, i >> 2);
         float4 n2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!kMerge) n2 = philox_normal4(seed, d1, i >> 2);
+        if (kNext && !kMerge) n2 = philox_normal4(seed, d1, i >> 2);
         const float xi1[4] = {n1.x, n1.y, n1.z, n1.w}, xi2[4] = {n2.x, n2.y, n2.z, n2.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          substep_element<kFirst, true, kMerge>(x[j], x0[j], x0b[j], y[j], cp[j], known[j], xi1[j], xi2[j], rc, cn[j],
+          substep_element<kFirst, kNext, kMerge>(x[j], x0[j], x0b[j], y[j], cp[j], known[j], xi1[j], xi2[j], rc, cn[j],
                                                 te[j]);
         *reinterpret_cast<float4*>(a.x + i) = make_float4(x[0], x[1], x[2], x[3]);
-        *reinterpret_cast<float4*>(a.c + i) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        if (kNext || a.store_c) *reinterpret_cast<float4*>(a.c + i) = make_float4(cn[0], cn[1], cn[2], cn[3]);
       }
     }
     __syncthreads();  // every thread is done reading stage s
@@ -1091,7 +1091,7 @@ inline int tma_mode() { return g_opt_tma; }  // 1 (default) = when eligible, 0 =
 
 // The TMA-staged variant needs 16-byte aligned slices: spatial a multiple of 16 (mask slices) and no
 // side outputs; only worth it when there are enough tiles to keep a persistent grid busy.
-template <bool kFirst, bool kMerge, int kTile, int kStages, int kMinBlocks>
+template <bool kFirst, bool kNext, bool kMerge, int kTile, int kStages, int kMinBlocks>
 int launch_substep_tma_cfg(const SubstepArgs& a, cudaStream_t s) {
   static int sms = 0;
   if (sms == 0) {
@@ -1102,7 +1102,7 @@ int launch_substep_tma_cfg(const SubstepArgs& a, cudaStream_t s) {
   const size_t smem = sizeof(TmaStage<kTile>) * kStages;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(substep_tma_kernel<kFirst, kMerge, kTile, kStages, kMinBlocks>,
+    cudaFuncSetAttribute(substep_tma_kernel<kFirst, kNext, kMerge, kTile, kStages, kMinBlocks>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
@@ -1112,21 +1112,24 @@ int launch_substep_tma_cfg(const SubstepArgs& a, cudaStream_t s) {
   tg.n_tiles = (a.g.total / a.g.spatial.d) * tg.tiles_per_channel;
   unsigned grid = (unsigned)sms * (unsigned)kMinBlocks;
   if (grid > tg.n_tiles) grid = tg.n_tiles;
-  launch_kernel_smem(substep_tma_kernel<kFirst, kMerge, kTile, kStages, kMinBlocks>, dim3(grid), smem, s, a, tg);
+  launch_kernel_smem(substep_tma_kernel<kFirst, kNext, kMerge, kTile, kStages, kMinBlocks>, dim3(grid), smem, s, a, tg);
   return check_launch();
 }
 
 // tile / ring geometry: "tma" option value 1 (default) = 2048-element tiles, 2 stages, 2 CTAs per SM;
 // 2, 3, 4 are the alternatives measured in profiles/README.md
-template <bool kFirst, bool kMerge>
+template <bool kFirst, bool kNext, bool kMerge>
 int launch_substep_tma(const SubstepArgs& a, cudaStream_t s) {
-  switch (tma_mode()) {
-    case 2: return launch_substep_tma_cfg<kFirst, kMerge, 1024, 4, 2>(a, s);
-    case 3: return launch_substep_tma_cfg<kFirst, kMerge, 4096, 2, 1>(a, s);
-    case 4: return launch_substep_tma_cfg<kFirst, kMerge, 2048, 4, 1>(a, s);
-    case 5: return launch_substep_tma_cfg<kFirst, kMerge, 1024, 3, 3>(a, s);
-    default: return launch_substep_tma_cfg<kFirst, kMerge, 2048, 2, 2>(a, s);
+  if (kNext && !kFirst && kMerge) {  // the steady kernel: alternative geometries stay selectable for measurement
+    switch (tma_mode()) {
+      case 2: return launch_substep_tma_cfg<kFirst, kNext, kMerge, 1024, 4, 2>(a, s);
+      case 3: return launch_substep_tma_cfg<kFirst, kNext, kMerge, 4096, 2, 1>(a, s);
+      case 4: return launch_substep_tma_cfg<kFirst, kNext, kMerge, 2048, 4, 1>(a, s);
+      case 5: return launch_substep_tma_cfg<kFirst, kNext, kMerge, 1024, 3, 3>(a, s);
+      default: break;
+    }
   }
+  return launch_substep_tma_cfg<kFirst, kNext, kMerge, 2048, 2, 2>(a, s);
 }
 
 inline bool tma_eligible(const SubstepArgs& a) {
@@ -1138,11 +1141,13 @@ inline bool tma_eligible(const SubstepArgs& a) {
 template <int N, int kRng>
 int launch_substep_vec(const SubstepArgs& a, bool first, bool next, bool merge, cudaStream_t s) {
   const unsigned grid = blocks_for((a.g.total + N - 1) / N);
-  if (N == 4 && kRng == LP_RNG_PHILOX && next && tma_eligible(a)) {
-    if (first && merge) return launch_substep_tma<true, true>(a, s);
-    if (first) return launch_substep_tma<true, false>(a, s);
-    if (merge) return launch_substep_tma<false, true>(a, s);
-    return launch_substep_tma<false, false>(a, s);
+  if (N == 4 && kRng == LP_RNG_PHILOX && tma_eligible(a)) {
+    if (first && next && merge) return launch_substep_tma<true, true, true>(a, s);
+    if (first && next) return launch_substep_tma<true, true, false>(a, s);
+    if (next && merge) return launch_substep_tma<false, true, true>(a, s);
+    if (next) return launch_substep_tma<false, true, false>(a, s);
+    if (first) return launch_substep_tma<true, false, false>(a, s);
+    return launch_substep_tma<false, false, false>(a, s);
   }
   if (merge && kRng == LP_RNG_PHILOX) {
     if (first) launch_kernel(substep_kernel<N, LP_RNG_PHILOX, true, true, true>, dim3(grid), s, a);
