@@ -166,3 +166,21 @@ def test_oversized_and_malformed_geometry_is_refused_before_any_launch():
     assert lib.lp_epilogue_f32(fake, fake, fake, fake, C.byref(empty), None) == 0
     assert lib.lp_substep_f32(fake, fake, fake, fake, fake, fake, None, None, fake, C.byref(empty), C.byref(r), 9, None) == 1
     assert lib.lp_set_option(b"no-such-option", 1) == 1
+
+
+def test_host_schedule_reproduces_the_reference_step_counts():
+    """runner.HostSchedule (the sync-free schedule of SURVEY 8f rank 3) against the oracle's per-step logic."""
+    from lanpaint_b200.runner import HostSchedule, karras_sigmas
+    ks = karras_sigmas(20)
+    assert torch.allclose(torch.tensor(ks), O.karras_sigmas(20), rtol=0, atol=0)
+    for n, subs, calls in ((5, 53, 73), (10, 106, 126), (0, 0, 20)):
+        sched = HostSchedule(ks, batch=3, n_inner=n)
+        assert (sched.substeps, sched.model_calls) == (subs, calls)
+        sig = O.karras_sigmas(20)
+        for i, st in enumerate(sched.steps):
+            s = sig[i] * torch.ones(3)
+            tm = O.times_from_sigma(s, False)
+            assert st.n_inner == O.inner_steps_for(s, sig, tm.abt, n)
+            assert all(torch.equal(a, b) for a, b in zip(st.times, tm))
+            assert st.sigma == float(sig[i]) and st.sigma_next == float(sig[i + 1])
+    assert [st.n_inner for st in HostSchedule(ks, 1, 5).steps] == [5] * 7 + [4, 4, 3, 3, 2, 1, 1] + [0] * 6
