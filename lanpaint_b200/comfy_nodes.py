@@ -174,7 +174,16 @@ def reshape_mask(input_mask, output_shape, video_inpainting=False):
 
 
 def prepare_mask(noise_mask, shape, device, video_inpainting=False):
-    return reshape_mask(noise_mask, shape, video_inpainting).to(device)
+    """Same values and shape as the reference's prepare_mask (nodes.py:119-130).  When the source mask has a
+    single channel the result is that channel moved to `device` and *expanded* (stride 0) over the latent's
+    channels instead of repeated: 1/C of the bytes cross PCIe, and `_latent_mask` can see without a device
+    read-back that one uint8 per spatial site is enough."""
+    m = noise_mask
+    one_channel = m.ndim <= 3 or m.shape[1] == 1
+    if one_channel and len(shape) >= 3 and shape[1] > 1:
+        compact = reshape_mask(m, (shape[0], 1) + tuple(shape[2:]), video_inpainting).to(device)
+        return compact.expand(tuple(shape))
+    return reshape_mask(m, shape, video_inpainting).to(device)
 
 
 # =============================================================================================
@@ -257,9 +266,12 @@ class KSamplerX0Inpaint:
         """1 - (denoise_mask > 0.5), packed once per distinct mask tensor (nodes.py:281-283)."""
         packed = self._mask_cache.get(denoise_mask)
         if packed is None:
-            known = denoise_mask <= 0.5
-            # prepare_mask repeats one spatial mask over the channels; if so keep a single copy
-            # (1/C byte per latent element).  One sync per distinct mask tensor, not per outer step.
+            m = denoise_mask
+            if m.ndim == like.ndim and m.shape[1] > 1 and m.stride(1) == 0:
+                m = m[:, :1]          # our prepare_mask: one spatial mask expanded over the channels
+            known = m <= 0.5
+            # a mask some other node materialised per channel: check once whether the channels agree (one
+            # read-back per distinct mask tensor, not per outer step) and keep 1/C byte per latent element
             if known.ndim == like.ndim and known.shape[1] > 1 and bool((known == known[:, :1]).all()):
                 known = known[:, :1]
             packed = pack_mask(known, like)
@@ -309,11 +321,22 @@ class KSamplerX0Inpaint:
 
 
 class KSAMPLER(comfy.samplers.KSAMPLER):
-    """KSAMPLER.sample replacement (nodes.py:318-379): builds the per-sigma wrapper and the engine."""
+    """KSAMPLER.sample replacement (nodes.py:318-379): builds the per-sigma wrapper and the engine.
+
+    Two launch strategies behind the same call:
+      * the sampler is plain Euler (what the node recommends) and nothing needs host code inside an outer
+        step: the whole sampler loop is run by `runner.GraphedJob` -- host-computed schedule, Euler update and
+        next replace step fused into the step-boundary kernel, CUDA graphs (one per outer step when ComfyUI
+        passed a progress/preview callback, one for the whole job otherwise) cached across sample() calls;
+      * anything else (the other 21 samplers, early stop, AV packs, mask schedules): k-diffusion's own loop
+        calls the per-sigma wrapper, which replays one CUDA graph per outer step.
+    Either way the first job of a configuration launches eagerly and the graphs are captured when the same
+    configuration comes back, so no model evaluation is ever spent on a warm-up pass."""
 
     def sample(self, model_wrap, sigmas, extra_args, callback, noise, latent_image=None, denoise_mask=None,
                disable_pbar=False):
         extra_args["denoise_mask"] = denoise_mask
+        LAST_RUN.update(mode=None, fused=False, job=None, events=None)
         model_k = KSamplerX0Inpaint(model_wrap, sigmas)
         model_k.latent_image = latent_image
         if self.inpaint_options.get("random", False):
@@ -326,33 +349,209 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
         is_flow = base.model_type in FLOW_MODEL_TYPES
         patcher = model_wrap.model_patcher
         model_wrap.cfg_BIG = 1.0 if is_flux else patcher.LanPaint_cfg_BIG
-        noise = base.model_sampling.noise_scaling(sigmas[0], noise, latent_image, self.max_denoise(model_wrap, sigmas))
+        max_denoise = self.max_denoise(model_wrap, sigmas)
+        x_init = base.model_sampling.noise_scaling(sigmas[0], noise, latent_image, max_denoise)
         layout = getattr(model_wrap, "minimax_h3_audio", None)
         if layout is not None and time_shift_sigma is not None:  # mark the audio rows of the flat pack (nodes.py:340-349)
             latent_shapes, shift_v, shift_a = layout
             video_n = math.prod(latent_shapes[0][1:])
-            indicator = torch.zeros(noise.shape, dtype=torch.float32, device=noise.device)
+            indicator = torch.zeros(x_init.shape, dtype=torch.float32, device=x_init.device)
             indicator[..., video_n:] = 1.0
             model_k.audio_indicator = indicator
             model_k.audio_shifts = (shift_v, shift_a)
         model_options = extra_args.get("model_options", {}) or {}
-        model_k.PaintMethod = LanPaint(
-            model_k.inner_model, patcher.LanPaint_NumSteps, patcher.LanPaint_Friction, patcher.LanPaint_Lambda,
-            patcher.LanPaint_Beta, patcher.LanPaint_StepSize, IS_FLUX=is_flux, IS_FLOW=is_flow,
-            EarlyStopThreshold=getattr(patcher, "LanPaint_InnerThreshold", 0.0),
-            EarlyStopPatience=getattr(patcher, "LanPaint_InnerPatience", 1),
-            EarlyStopHook=model_options.get("lanpaint_semantic_hook", None),
-            MinStepFrac=getattr(patcher, "LanPaint_MinStepFrac", 1.0))
-        model_k.LanPaint_early_stop = patcher.LanPaint_EarlyStop
-        model_k.LanPaint_min_step_frac = getattr(patcher, "LanPaint_MinStepFrac", 1.0)
+        opts = model_options.get("lanpaint_b200", {}) or {}
+        hyper = dict(NSteps=patcher.LanPaint_NumSteps, Friction=patcher.LanPaint_Friction,
+                     Lambda=patcher.LanPaint_Lambda, Beta=patcher.LanPaint_Beta, StepSize=patcher.LanPaint_StepSize,
+                     IS_FLUX=is_flux, IS_FLOW=is_flow,
+                     EarlyStopThreshold=getattr(patcher, "LanPaint_InnerThreshold", 0.0),
+                     EarlyStopPatience=getattr(patcher, "LanPaint_InnerPatience", 1),
+                     MinStepFrac=getattr(patcher, "LanPaint_MinStepFrac", 1.0))
+        early_stop = patcher.LanPaint_EarlyStop
+        use_graph = _graphs_enabled(opts)
+        entry = _ENGINES.lookup(model_wrap, x_init, model_k.sigmas_host, hyper, early_stop, max_denoise, opts,
+                                model_options, callback is not None) if use_graph else None
+        engine = entry.engine if entry is not None else None
+        if engine is None:
+            engine = LanPaint(model_k.inner_model, EarlyStopHook=model_options.get("lanpaint_semantic_hook", None),
+                              rng=opts.get("rng", "torch"), batched_replace=opts.get("batched_replace", "reference"),
+                              cuda_graph=use_graph, graph_after=int(opts.get("graph_after", 1)), **hyper)
+            if entry is not None:
+                entry.engine = engine
+                engine.graph_model_token = "node-cache"   # the entry's key already pins model, conds and scales
+        else:  # a configuration seen before: same engine (and its graphs), this call's guider and hook
+            engine.inner_model = model_k.inner_model
+            engine.early_stop_hook = model_options.get("lanpaint_semantic_hook", None)
+            engine.reset_counters()
+        model_k.PaintMethod = engine
+        model_k.LanPaint_early_stop = early_stop
+        model_k.LanPaint_min_step_frac = hyper["MinStepFrac"]
         total_steps = len(sigmas) - 1
-        k_callback = None
-        if callback is not None:
-            k_callback = lambda d: callback(d["i"], d["denoised"], d["x"], total_steps)  # noqa: E731
-        samples = self.sampler_function(model_k, noise, sigmas, extra_args=extra_args, callback=k_callback,
-                                        disable=disable_pbar, **self.extra_options)
-        self.last_engine = model_k.PaintMethod
+        timing = None
+        if opts.get("timing"):   # bench/profiling: device time of the sampler loop, inputs already on the device
+            timing = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            timing[0].record()
+
+        samples = None
+        if opts.get("fused_sampler", True) and self._fused_euler_ok(model_k, denoise_mask, model_options, engine):
+            samples = self._fused_euler(model_k, entry, engine, x_init, latent_image, denoise_mask, model_options,
+                                        extra_args.get("seed"), is_flux or is_flow, early_stop, callback, total_steps,
+                                        use_graph, opts)
+        if samples is None:
+            k_callback = None
+            if callback is not None:
+                k_callback = lambda d: callback(d["i"], d["denoised"], d["x"], total_steps)  # noqa: E731
+            samples = self.sampler_function(model_k, x_init, sigmas, extra_args=extra_args, callback=k_callback,
+                                            disable=disable_pbar, **self.extra_options)
+        self.last_engine = engine
+        if timing is not None:
+            timing[1].record()
+            LAST_RUN["events"] = timing
         return base.model_sampling.inverse_noise_scaling(sigmas[-1], samples)
+
+    # ---- plain Euler: the sampler loop as one launch sequence ---------------------------------------
+    def _fused_euler_ok(self, model_k, denoise_mask, model_options, engine) -> bool:
+        """True when k-diffusion's sample_euler around the per-sigma wrapper is exactly the host-owned loop of
+        runner.GraphedJob: default Euler (no churn), an inpainting mask, nothing that runs host code or changes
+        the mask inside an outer step."""
+        fn = self.sampler_function
+        if getattr(fn, "__name__", "") != "sample_euler":
+            return False
+        eo = self.extra_options or {}
+        if float(eo.get("s_churn", 0.0) or 0.0) != 0.0 or float(eo.get("s_noise", 1.0) or 1.0) != 1.0:
+            return False
+        if denoise_mask is None or model_k.audio_indicator is not None:
+            return False
+        if "denoise_mask_function" in model_options or model_options.get("callback") is not None:
+            return False
+        if float(engine.early_stop_threshold or 0.0) > 0.0 or isinstance(model_options.get("lanpaint_semantic_stop"), dict):
+            return False
+        if engine.rng not in ("torch", "philox"):
+            return False
+        sig = model_k.sigmas_host
+        return len(sig) >= 2 and all(v > 0.0 for v in sig[:-1])
+
+    def _fused_euler(self, model_k, entry, engine, x_init, latent_image, denoise_mask, model_options, seed, flow,
+                     early_stop, callback, total_steps, use_graph, opts):
+        from .runner import GraphedJob, HostSchedule
+        if not x_init.is_cuda:
+            raise RuntimeError("lanpaint_b200 needs the latent on a CUDA device: there is no CPU or eager fallback")
+        if engine._noise_is_zero(model_k.noise):   # add_noise disabled: fresh noise every outer step (lanpaint.py:51-52)
+            return None
+        B = x_init.shape[0]
+        job = entry.job if entry is not None else None
+        if job is None:
+            sched = HostSchedule(model_k.sigmas_host, B, engine.n_steps, flow, early_stop, engine.min_step_frac)
+            try:
+                job = GraphedJob(engine, sched, tuple(x_init.shape), x_init.device, flow=flow, external_init=True,
+                                 first_replace_noop=False)
+            except ValueError:     # noise_scaling is not a linear form: the per-sigma wrapper calls it instead
+                return None
+            if entry is not None:
+                entry.job = job
+        job.model_options, job.seed = model_options, seed
+        pm = model_k._latent_mask(denoise_mask, x_init)
+        runs = entry.runs if entry is not None else 0
+        after = int(opts.get("graph_after", 1))
+        captures = job.captures
+        if not use_graph or entry is None or entry.graph_failed or runs < after:
+            mode = "eager"
+        else:
+            mode = "steps" if callback is not None else "job"
+        try:
+            out = job.run(latent_image, model_k.noise, pm, x_init=x_init, callback=callback, mode=mode,
+                          warm=after <= 0)
+        except Exception as e:
+            if mode == "eager":
+                raise
+            import warnings
+            from .engine import _repair_generator_after_failed_capture
+            warnings.warn(f"lanpaint_b200: CUDA-graph capture of the sampler loop failed ({type(e).__name__}: {e}); "
+                          "running eagerly")
+            _repair_generator_after_failed_capture(x_init.device)
+            entry.graph_failed = True
+            job._graphs = {}
+            engine.reset_counters()
+            out = job.run(latent_image, model_k.noise, pm, x_init=x_init, callback=callback, mode="eager")
+        if entry is not None:
+            entry.runs += 1
+            entry.last_mode = mode
+            if job.captures != captures:   # graphs captured during this call read through this call's guider
+                entry.pinned.append((model_k.inner_model, model_options))
+        LAST_RUN.update(mode=mode, fused=True, job=job)
+        return out if out.dtype == x_init.dtype else out.to(x_init.dtype)
+
+
+# =============================================================================================
+# engines (and their CUDA graphs) kept across sample() calls
+# =============================================================================================
+def _graphs_enabled(opts) -> bool:
+    import os
+    if os.environ.get("LANPAINT_B200_GRAPH", "1") == "0":
+        return False
+    return bool(opts.get("cuda_graph", True))
+
+
+def _weights_fingerprint(model_wrap):
+    """Where the network's parameters live right now.  A captured graph holds raw pointers into them: if
+    ComfyUI off-loaded and re-loaded the model (new addresses) the cached graphs must be dropped."""
+    net = getattr(getattr(model_wrap, "inner_model", None), "diffusion_model", None)
+    if isinstance(net, torch.nn.Module):
+        return tuple(p.data_ptr() for p in net.parameters())
+    return id(net)
+
+
+class _EngineEntry:
+    __slots__ = ("engine", "job", "runs", "graph_failed", "last_mode", "weights", "keep", "pinned")
+
+    def __init__(self):
+        self.engine = self.job = None
+        self.pinned = []
+        self.runs = 0
+        self.graph_failed = False
+        self.last_mode = None
+        self.weights = None
+        self.keep = None
+
+
+class _EngineCache:
+    """A few recently used (engine, GraphedJob) pairs keyed by everything a captured graph bakes in: the
+    ModelPatcher, the conditioning objects, both guidance scales, latent shape and device, the sigma schedule,
+    every hyper-parameter, the model_options the network reads, whether a callback wants the denoised latent.
+    The entry keeps the objects named by id() alive, so an id in the key can never be recycled."""
+
+    def __init__(self, capacity: int = 4):
+        self.capacity = capacity
+        self.entries = {}
+
+    def lookup(self, model_wrap, x, sigmas_host, hyper, early_stop, max_denoise, opts, model_options, has_callback):
+        from .engine import options_fingerprint
+        conds = getattr(model_wrap, "original_conds", None) or getattr(model_wrap, "conds", {}) or {}
+        pos, neg = conds.get("positive"), conds.get("negative")
+        net_opts = {k: v for k, v in model_options.items() if k != "lanpaint_b200"}
+        key = (id(model_wrap.model_patcher), id(pos), id(neg), float(model_wrap.cfg), float(model_wrap.cfg_BIG),
+               str(x.device), tuple(x.shape), str(x.dtype), tuple(sigmas_host), tuple(sorted(hyper.items())),
+               early_stop, bool(max_denoise), options_fingerprint(opts), options_fingerprint(net_opts),
+               bool(has_callback))
+        entry = self.entries.pop(key, None)
+        weights = _weights_fingerprint(model_wrap)
+        if entry is not None and entry.weights != weights:
+            entry = None                       # the model moved: graphs captured against it are dead
+        if entry is None:
+            entry = _EngineEntry()
+            entry.weights = weights
+        entry.keep = (model_wrap, model_wrap.model_patcher, pos, neg, model_options)
+        self.entries[key] = entry              # most recently used last
+        while len(self.entries) > self.capacity:
+            self.entries.pop(next(iter(self.entries)))
+        return entry
+
+    def clear(self):
+        self.entries.clear()
+
+
+_ENGINES = _EngineCache()
+LAST_RUN = {"mode": None, "fused": False, "job": None, "events": None}   # how the most recent sample call was launched
 
 
 _override_active = False

@@ -132,6 +132,23 @@ def pack_mask(latent_mask: torch.Tensor, like: torch.Tensor) -> PackedMask:
     return PackedMask(data, Cc * spatial, spatial)
 
 
+def options_fingerprint(o, depth: int = 0):
+    """A cheap structural identity of a model_options-like object: primitives by value, containers two
+    levels deep, everything else (tensors, callables, patches) by object identity.  Graph caches key on it
+    because a captured graph bakes in whatever the model read from these options at capture time."""
+    if isinstance(o, (str, int, float, bool, type(None))):
+        return o
+    if isinstance(o, dict) and depth < 3:
+        return tuple((str(k), options_fingerprint(v, depth + 1)) for k, v in sorted(o.items(), key=lambda kv: str(kv[0])))
+    if isinstance(o, (list, tuple)) and depth < 3:
+        return tuple(options_fingerprint(v, depth + 1) for v in o)
+    if isinstance(o, torch.Tensor) and o.numel() <= 1024:
+        # small tensors (ComfyUI's transformer_options["sample_sigmas"], ...) are re-created per job with
+        # the same values: identify them by content
+        return ("tensor", tuple(o.shape), str(o.dtype), tuple(o.detach().reshape(-1).tolist()))
+    return id(o)
+
+
 def _tensor_key(t: torch.Tensor):
     """What can change under us without the object changing: storage address, layout, in-place writes.
     Inference tensors (ComfyUI runs nodes under torch.inference_mode) have no version counter."""
@@ -189,13 +206,19 @@ class LanPaint:
                       variance (identical chain in distribution, half the RNG work)
       cuda_graph      False | True: capture the whole outer step (model calls included) into one
                       CUDA graph per (shape, sub-step count) and replay it; falls back to eager
-                      launches if the model is not capture-safe
+                      launches if the model is not capture-safe.  The graph bakes in the model object,
+                      whatever it read from model_options (both are part of the cache key) and `seed`
+                      (by value; not part of the key), and reads latent_image / noise / mask from static
+                      copies refreshed whenever the source tensor changes identity or version
+      graph_after     0: capture at first use (one warm-up pass of the step on a side stream first);
+                      k > 0: run a configuration eagerly the first k times it is seen and capture it the
+                      next time, without a warm-up pass (what the node path uses: no wasted model calls)
     """
 
     def __init__(self, Model, NSteps, Friction, Lambda, Beta, StepSize, IS_FLUX=False, IS_FLOW=False,
                  EarlyStopThreshold=0.0, EarlyStopPatience=1, EarlyStopHook=None, MinStepFrac=0.0, *,
                  rng="torch", batched_replace="reference", replace_mode="probe", cuda_graph=False,
-                 merge_noise=True):
+                 merge_noise=True, graph_after=0):
         self.n_steps = NSteps
         self.chara_lamb = Lambda
         self.IS_FLUX = IS_FLUX
@@ -214,8 +237,16 @@ class LanPaint:
         self.replace_mode = replace_mode
         self.cuda_graph = cuda_graph
         self.merge_noise = merge_noise
+        # capture a configuration the (graph_after+1)-th time it is seen; 0 = immediately, with a warm-up pass
+        self.graph_after = graph_after
+        # part of the graph cache key in place of id(inner_model) when the caller (the node layer) already
+        # guarantees that a re-bound inner_model is functionally the one the graphs were captured with
+        self.graph_model_token = None
         self._graphs = {}
+        self._graph_seen = {}
+        self._graph_keep = []
         self._graph_statics = {}
+        self.max_live_shapes = 4   # workspaces / static graph buffers kept per (device, shape)
         # statistics a caller (bench, tests) can read back
         self.launches = 0
         self.model_calls = 0
@@ -223,9 +254,13 @@ class LanPaint:
         self._mask_cache = _IdentityCache()
         self._noise_zero_cache = _IdentityCache()
         self._av_cache = _IdentityCache()
+        self._av_mask_cache = _IdentityCache()
         self._ws = {}
         self.kernel_timer = None  # set to a list to collect (flags, start_event, stop_event) per substep launch
         _native.load()  # fail at construction, loudly, if the CUDA library is absent
+
+    def reset_counters(self):
+        self.launches = self.model_calls = self.substeps_done = 0
 
     # ---- small helpers kept for API compatibility (lanpaint.py:23-43) ----------
     def add_none_dims(self, array):
@@ -262,7 +297,9 @@ class LanPaint:
                 "c": torch.empty_like(like, dtype=torch.float32, memory_format=torch.contiguous_format),
                 "table_dev": torch.empty((rows, _native.TABLE_STRIDE), dtype=torch.float32, device=like.device),
             }
-            self._ws = {key: ws}  # one live shape at a time
+            while len(self._ws) >= self.max_live_shapes:   # a few live shapes (alternating requests), oldest out
+                self._ws.pop(next(iter(self._ws)))
+            self._ws[key] = ws
         return ws
 
     # ---- replace-step linear form (lanpaint.py:85-94) ----------------------------
@@ -311,13 +348,16 @@ class LanPaint:
             opts = model_options.get("lanpaint_b200", {}) or {}
         rng = opts.get("rng", self.rng)
 
-        # lanpaint.py:51-52 -- add_noise disabled: a fresh noise image every outer step
-        if self._noise_is_zero(self.noise):
-            self.noise = self._regen_noise(self.noise, rng)
-        if n_steps is None:
-            n_steps = self.n_steps
-        return self.LanPaint(x, sigma, latent_mask, current_times, n_steps, model_options, seed,
-                             self.IS_FLUX, self.IS_FLOW, _opts=opts)
+        # every launch below goes to the current stream of x's device: make that device current for the call
+        # (a process that drives several GPUs -- ComfyUI multi-GPU, thread-per-device replicas -- may not have)
+        with torch.cuda.device(x.device):
+            # lanpaint.py:51-52 -- add_noise disabled: a fresh noise image every outer step
+            if self._noise_is_zero(self.noise):
+                self.noise = self._regen_noise(self.noise, rng)
+            if n_steps is None:
+                n_steps = self.n_steps
+            return self.LanPaint(x, sigma, latent_mask, current_times, n_steps, model_options, seed,
+                                 self.IS_FLUX, self.IS_FLOW, _opts=opts)
 
     def _noise_is_zero(self, noise: torch.Tensor) -> bool:
         hit = self._noise_zero_cache.get(noise)
@@ -401,7 +441,7 @@ class LanPaint:
         sigma_dev = sigma.to(dev)
         out = torch.empty_like(xm)
         done = self._launch_sequence(xm, y, nz, pm, dims, tab, t_model, sigma_dev, ws["c"], out, active, plan,
-                                     form is None, model_options, seed, stopper, None)
+                                     form is None, model_options, seed, stopper, None, current_times=current_times)
         plan.finish()
         self.substeps_done += done
         if xm is not input_x:
@@ -411,7 +451,7 @@ class LanPaint:
     # ---- the launch sequence of one outer step (shared by the eager path and graph capture) ----
     def _launch_sequence(self, xm, y, nz, pm, dims, tab, t_model, sigma_dev, cbuf, out, active, plan, call_scaling,
                          model_options, seed, stopper, rng_state, euler_coef=None, skip_prologue=False,
-                         next_table=None):
+                         next_table=None, current_times=None):
         lib = _native.load()
         dev = xm.device
         stream = _P(_stream_ptr(dev))
@@ -492,8 +532,17 @@ class LanPaint:
             self.launches += 1
             done += 1
             inv_s = tab[:, _native.T_INVS].reshape((-1,) + (1,) * (xm.ndim - 1))
-            ctx = {"step": i, "steps_done": i + 1, "n_steps": active, "mask": pm, "latent_image": y,
-                   "current_times": None, "seed": seed}
+            # what a user distance_fn may read (lanpaint.py:121-129): the float latent_mask of the latent's
+            # shape and the (VE, abt, flow_t) triple -- unpacked only when such a hook exists
+            ctx_mask = pm
+            if stopper.has_custom_distance_fn:
+                if getattr(stopper, "_ctx_mask", None) is None:
+                    m = pm.data.reshape(-1).to(torch.float32)
+                    stopper._ctx_mask = (m.reshape(xm.shape) if m.numel() == xm.numel()
+                                         else pm.data.to(torch.float32).expand(xm.shape))
+                ctx_mask = stopper._ctx_mask
+            ctx = {"step": i, "steps_done": i + 1, "n_steps": active, "mask": ctx_mask, "latent_image": y,
+                   "current_times": current_times, "seed": seed}
             stop = stopper.step(i=i, n_steps=active, x_before=x_before if first else None, x_after=xm,
                                 x0_prev=x0e_prev, x0_cur=x0e, table=tab,
                                 custom_prev=(lambda: custom_prev * inv_s) if custom_prev is not None else None,
@@ -505,6 +554,8 @@ class LanPaint:
         # final denoise + known-region paste (lanpaint.py:151-157)
         out_heads = self.inner_model(xm, sigma_dev, model_options=model_options, seed=seed)
         self.model_calls += 1
+        if isinstance(out_heads, CfgPair) and (next_table is not None or out is None):
+            out_heads = (out_heads.uncond + (out_heads.cond - out_heads.uncond) * out_heads.cfg,)
         if isinstance(out_heads, CfgPair):
             cd, uc = _as_operand(out_heads.cond, xm), _as_operand(out_heads.uncond, xm)
             rc = lib.lp_epilogue_cfg_f32(_P(cd.data_ptr()), _P(uc.data_ptr()), C.c_float(out_heads.cfg),
@@ -545,11 +596,23 @@ class LanPaint:
         then runs eagerly)."""
         dev = x.device
         B = x.shape[0]
+        # what a captured graph bakes in besides the buffers: the launch geometry, everything the model read
+        # from model_options, and the model object itself.  `seed` is handed to the model by value at capture;
+        # none of ComfyUI's stock models consume it -- a model that does needs cuda_graph=False.
         key = (dev, tuple(x.shape), active, plan.mode, bool(call_scaling), tuple(sigma_shape),
-               pm.row_stride, pm.channel_stride)
+               pm.row_stride, pm.channel_stride,
+               id(self.inner_model) if self.graph_model_token is None else self.graph_model_token,
+               options_fingerprint(model_options))
         g = self._graphs.get(key)
         if g is False:
             return None
+        if g is None and self.graph_after > 0:
+            # first sight of this configuration: run it eagerly (that IS the work; nothing is spent on a
+            # warm-up pass) and capture when it comes back
+            seen = self._graph_seen.get(key, 0)
+            if seen < self.graph_after:
+                self._graph_seen[key] = seen + 1
+                return None
         st = self._graph_static(x, y, nz, pm, B)
         n_par = B * _native.TABLE_STRIDE + 2 * B + 4
         # ---- the dynamic block: [table | t_model | sigma | seed, base (2 x u64 in 4 float slots)] ----
@@ -560,7 +623,11 @@ class LanPaint:
         host[o + B:o + 2 * B] = sigma_h
         host[o + 2 * B:].view(np.uint64)[:] = plan.state_words()
         if g is None:
-            g = self._capture(key, st, dims, B, host, sigma_shape, active, plan, call_scaling, model_options, seed)
+            g = self._capture(key, st, dims, B, host, sigma_shape, active, plan, call_scaling, model_options, seed,
+                              warm=self.graph_after <= 0)
+            # keeps the ids inside the key from being recycled, and whatever the captured model call reads
+            # through this guider (conditioning tensors) alive at the addresses the graph baked in
+            self._graph_keep.append((model_options, self.inner_model))
             if g is None:
                 self._graphs[key] = False
                 return None
@@ -581,18 +648,23 @@ class LanPaint:
             st = {"x": torch.empty_like(x, dtype=torch.float32, memory_format=torch.contiguous_format),
                   "y": torch.empty_like(y), "nz": torch.empty_like(nz), "mask": torch.empty_like(pm.data),
                   "c": torch.empty_like(y), "src": [None, None, None]}
-            self._graph_statics = {key: st}
-            self._graphs = {}
+            while len(self._graph_statics) >= self.max_live_shapes:
+                old = next(iter(self._graph_statics))
+                self._graph_statics.pop(old)
+                self._graphs = {k: g for k, g in self._graphs.items() if (k[0], k[1]) != old}
+            self._graph_statics[key] = st
         for slot, (name, src) in enumerate((("y", y), ("nz", nz), ("mask", pm.data))):
-            if st["src"][slot] is None or not st["src"][slot].matches(src):
+            # inference tensors have no version counter: an in-place edit cannot be seen, so re-copy them
+            if st["src"][slot] is None or not st["src"][slot].matches(src) or st["src"][slot].key[1] is None:
                 if st[name].shape != src.shape:
                     st[name] = torch.empty_like(src)
-                    self._graphs = {}
+                    self._graphs = {k: g for k, g in self._graphs.items() if (k[0], k[1]) != key}
                 st[name].copy_(src)
                 st["src"][slot] = _Ident(src)
         return st
 
-    def _capture(self, key, st, dims, B, host, sigma_shape, active, plan, call_scaling, model_options, seed):
+    def _capture(self, key, st, dims, B, host, sigma_shape, active, plan, call_scaling, model_options, seed,
+                 warm=True):
         dev = st["x"].device
         params = torch.from_numpy(host).to(dev)
         o = B * _native.TABLE_STRIDE
@@ -613,11 +685,12 @@ class LanPaint:
                                   rel, call_scaling, model_options, seed, None, rng_state)
         try:
             timer, self.kernel_timer = self.kernel_timer, None
-            side = torch.cuda.Stream(device=dev)
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):
-                body()  # warm-up outside capture: lazy inits, allocator
-            torch.cuda.current_stream(dev).wait_stream(side)
+            if warm:
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    body()  # warm-up outside capture: lazy inits, allocator
+                torch.cuda.current_stream(dev).wait_stream(side)
             self.launches, self.model_calls = counts
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
@@ -727,6 +800,14 @@ class LanPaint:
         self._av_cache.put(ai, split)
         return split
 
+    def _av_blended_times(self, current_times, dev):
+        """(VE, abt, flow_t) as the reference blends them for an AV pack (lanpaint.py:68-74); only built when
+        an early-stop hook may read ctx["current_times"]."""
+        VE, abt, flow_t = (t.to(dev) for t in current_times)
+        VE_a, abt_a, _ = (t.to(dev) for t in self.current_times_audio)
+        ai = self.audio_indicator.to(dev)
+        return _blend(VE, VE_a, ai), _blend(abt, abt_a, ai), flow_t
+
     def _av_call(self, x, sigma, latent_mask, current_times, n_steps, model_options, seed, flow, opts):
         """lanpaint.py:60-74,173-180: audio positions take (VE, abt) and the replace sigma from the audio
         schedule and pull the model's target back by `audio_correction`; everything else is unchanged.
@@ -761,12 +842,22 @@ class LanPaint:
         xm = x if (x.dtype == torch.float32 and x.is_contiguous()) else _f32c(x)
         y = _f32c(self.latent_image.to(dev))
         nz = _f32c(self.noise.to(dev))
-        pm = self._mask_cache.get(latent_mask) if isinstance(latent_mask, torch.Tensor) else None
-        if pm is None:
-            full = latent_mask.to(dev).expand(x.shape) if isinstance(latent_mask, torch.Tensor) else latent_mask
-            pm = pack_mask(full.reshape(1, 1, -1), xm.reshape(1, 1, -1))
-            self._mask_cache.put(latent_mask, pm)
-            self.launches += 1
+        # the flat pack is indexed line by line (dims below): the mask becomes one uint8 per element
+        if isinstance(latent_mask, PackedMask):      # what the node layer hands over (comfy_nodes._latent_mask)
+            pm = self._av_mask_cache.get(latent_mask.data)
+            if pm is None:
+                data = latent_mask.data
+                if data.numel() != x.numel():        # stored once per spatial site: repeat over the channels
+                    data = data.expand(x.shape)
+                pm = PackedMask(data.reshape(1, 1, -1).contiguous(), n_last, 0)
+                self._av_mask_cache.put(latent_mask.data, pm)
+        else:
+            pm = self._mask_cache.get(latent_mask)
+            if pm is None:
+                full = latent_mask.to(dev).expand(x.shape)
+                pm = pack_mask(full.reshape(1, 1, -1), xm.reshape(1, 1, -1))
+                self._mask_cache.put(latent_mask, pm)
+                self.launches += 1
         dims = _native.Dims(lines, n_last, n_last, n_last, 0, split)
         tab = torch.from_numpy(table_np).to(dev)
         t_model = t_model_src.reshape(-1).to(dev)
@@ -774,13 +865,22 @@ class LanPaint:
         plan = _DrawPlan(rng, xm, active)
         out = torch.empty_like(xm)
         cbuf = torch.empty_like(xm)
+        # lanpaint.py:104-111: the stopper sees the blended per-position abt; its mean is what scales the threshold
+        abt_blend = np.float32((split * np.float32(abt_v) + (n_last - split) * np.float32(abt_au)) / n_last)
+        flat = xm.reshape(1, 1, -1)
+        stopper = self._make_stopper(model_options, pm, flat, np.asarray([abt_blend]), dims)
+        times_blend = (VE_Sigma, abt, Flow_t) if stopper is None else self._av_blended_times(current_times, dev)
         done = self._launch_sequence(xm, y, nz, pm, dims, tab, t_model, sigma.to(dev), cbuf, out, active, plan, False,
-                                     model_options, seed, None, None)
+                                     model_options, seed, stopper, None, current_times=times_blend)
         plan.finish()
         self.substeps_done += done
         if xm is not x:
             x.copy_(xm)
         return out if out.dtype == x.dtype else out.to(x.dtype)
+
+
+def _blend(a, b, ai):
+    return a * (1 - ai) + b * ai
 
 
 def _repair_generator_after_failed_capture(dev: torch.device) -> None:

@@ -82,6 +82,30 @@ class SynthDenoiser:
         return (self._h0, self._h1) if self.two_heads else self._h0
 
 
+class SynthCondNet:
+    """`denoiser(x, sigma, cond) -> x0` for a ComfyUI-style BaseModel (bench / tests): the same pointwise
+    kernel as SynthDenoiser, one head per call, `cond` (a float standing in for CONDITIONING) shifts the
+    output.  One output buffer per distinct cond, reused across calls like a captured network's."""
+
+    def __init__(self, coef=(0.7, 0.1, 0.0)):
+        self.coef = tuple(float(c) for c in coef)
+        self._out = {}
+        self._lib = _native.load()
+        self.calls = 0
+
+    def __call__(self, x, sigma, cond):
+        c = float(cond)
+        key = (c, tuple(x.shape), x.device)
+        out = self._out.get(key)
+        if out is None:
+            out = self._out[key] = (torch.empty_like(x), (C.c_float * 5)(self.coef[0], self.coef[1], self.coef[2] + c, 0.0, 0.0))
+        rc = self._lib.lp_synth_denoiser_f32(C.c_void_p(x.data_ptr()), C.c_void_p(out[0].data_ptr()), None, x.numel(),
+                                             out[1], C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        _native.check(rc, "lp_synth_denoiser_f32")
+        self.calls += 1
+        return out[0]
+
+
 @dataclass
 class OuterStep:
     sigma: float
@@ -199,16 +223,27 @@ def time_steady_substep(engine, latent_image: torch.Tensor, mask, sigma: float, 
 
 class GraphedJob:
     """A whole inpaint job -- initial noise_scaling, every outer step (prologue, model calls, fused
-    sub-steps, epilogue) and the Euler updates between them -- captured ONCE as a single CUDA graph and
-    replayed per batch of requests.  Everything sigma-dependent is a device constant computed at
-    construction (one coefficient table per outer step), so a replay costs one 16-byte H2D copy (the RNG
-    position) plus the copies of the request's own inputs.  This is the serving configuration: fixed
-    schedule, fixed batch shape, a stream of request batches.
+    sub-steps, epilogue) and the Euler updates between them -- on static buffers, launched in one of
+    three ways that share ONE body (`_step`):
 
-    Semantics are exactly `euler_inpaint(engine, ...)` (asserted bit-for-bit by the tests)."""
+      mode "job"    the whole job is ONE CUDA graph (captured once, replayed per batch of requests);
+      mode "steps"  one CUDA graph per outer step, replayed in order with a host callback between them
+                    (ComfyUI's progress / preview callback wants the denoised latent of every step);
+      mode "eager"  plain launches (the first job of a configuration: nothing is wasted on warm-up).
+
+    Everything sigma-dependent is a device constant computed at construction (one coefficient table per
+    outer step), so a replay costs one 16-byte H2D copy (the RNG position) plus the copies of the
+    request's own inputs.  Used directly by hosts that own the sampler loop (serving: fixed schedule,
+    fixed batch shape, a stream of request batches) and by the node path (`comfy_nodes.KSAMPLER.sample`)
+    whenever the ComfyUI sampler is plain Euler, the configuration the reference recommends
+    (src/LanPaint/nodes.py:459 "Recommended: euler").
+
+    Semantics are exactly `euler_inpaint(engine, ...)`, i.e. k-diffusion's sample_euler around the
+    per-sigma wrapper (asserted bit-for-bit by the tests)."""
 
     def __init__(self, engine, sched: HostSchedule, shape, device, flow: bool = False, fused_euler: bool = True,
-                 l2_persist: bool = False):
+                 l2_persist: bool = False, model_options=None, seed=0, external_init: bool = False,
+                 first_replace_noop=None):
         import numpy as np
         from .engine import _DrawPlan
         self.fused_euler = fused_euler   # Euler update inside lp_epilogue_euler_f32 instead of two torch kernels
@@ -221,6 +256,8 @@ class GraphedJob:
         if engine.rng not in ("philox", "torch"):
             raise ValueError("GraphedJob needs an in-kernel RNG mode ('philox' or 'torch')")
         self.engine, self.sched, self.flow = engine, sched, flow
+        self.model_options, self.seed = model_options, seed
+        self.external_init = external_init   # run(x_init=...) supplies the initial state (node path: max_denoise etc.)
         self.device = torch.device(device)
         self.shape = tuple(shape)
         B = self.shape[0]
@@ -240,89 +277,173 @@ class GraphedJob:
             tms.append(flow_t if flow else ve)
             sgs.append(sig)
             self.active.append(st.n_inner if mean_half_dt(abt, hyper) > 0.0 else 0)
+        # draws consumed before outer step i (1 for sub-step 0, 2 for each later one): lets every outer step be
+        # captured on its own against ONE {seed, base} block that is refreshed once per job
+        self.draws_before = [0]
+        for n in self.active:
+            self.draws_before.append(self.draws_before[-1] + (2 * n - 1 if n > 0 else 0))
         self.tables = torch.from_numpy(np.stack(tabs)).to(dev)
         self.t_model = torch.from_numpy(np.stack(tms).astype(np.float32)).to(dev)
         self.sigma = torch.from_numpy(np.stack(sgs).astype(np.float32)).to(dev)
         self.sigma0 = torch.tensor(float(sched.sigmas[0]), device=dev)
         self.rng_state = torch.zeros(2, dtype=torch.int64, device=dev)
-        self.graph = None
-        self.draws = 0
+        if first_replace_noop is None:
+            # the first replace step is a no-op when the replace form is noise_scaling's own form at sigmas[0]
+            # (every known position of x already holds it); the reference's batched flow-form quirk differs
+            first_replace_noop = (not external_init) and (B == 1 or engine.batched_replace == "per_sample")
+        self.first_replace_noop = bool(first_replace_noop) and fused_euler
+        self._graphs = {}
+        self._dims = None
         self.launches = 0
         self.model_calls = 0
+        self.captures = 0
         self._plan_cls = _DrawPlan
 
-    def _body(self, pm, dims, plan):
-        eng = self.engine
-        sampling = eng.inner_model.inner_model.model_sampling
+    @property
+    def draws(self) -> int:
+        return self.draws_before[-1]
+
+    @property
+    def graph(self):
+        """The whole-job graph (None until the first mode="job" run)."""
+        return self._graphs.get(("job", False))
+
+    # ---- the body ------------------------------------------------------------------------------
+    def _init_state(self):
+        sampling = self.engine.inner_model.inner_model.model_sampling
         self.x.copy_(sampling.noise_scaling(self.sigma0, self.noise, self.y))
-        state = self.rng_state.data_ptr()
-        for i, st in enumerate(self.sched.steps):
-            coef = (st.sigma_next - st.sigma) / st.sigma
-            last = i + 1 == len(self.sched.steps)
-            # the first replace step is a no-op when the replace form is noise_scaling's own form at sigmas[0]
-            # (every position of x already holds it); only the reference's batched flow-form quirk differs
-            first_is_noop = self.fused_euler and i == 0 and (self.shape[0] == 1 or eng.batched_replace == "per_sample")
-            eng._launch_sequence(self.x, self.y, self.noise, pm, dims, self.tables[i], self.t_model[i], self.sigma[i],
-                                 self.c, None if self.fused_euler else self.out, self.active[i], plan, False, None, 0,
-                                 None, state, euler_coef=coef if self.fused_euler else None,
-                                 skip_prologue=(self.fused_euler and i > 0) or first_is_noop,
-                                 next_table=self.tables[i + 1] if (self.fused_euler and not last) else None)
-            if not self.fused_euler:
-                self.x.add_(self.x - self.out, alpha=coef)
 
-    def _capture(self, pm):
-        import numpy as np
+    def _step(self, i, plan, want_out):
         eng = self.engine
-        B = self.shape[0]
-        dims = _native.Dims(B, self.x.numel() // B, int(np.prod(self.shape[2:])), pm.row_stride, pm.channel_stride)
-        plan = self._plan_cls(eng.rng, self.x, 1).relative()
-        counts = (eng.launches, eng.model_calls)
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):
-            self._body(pm, dims, plan)
-        torch.cuda.current_stream(self.device).wait_stream(side)
-        plan.reset()
-        eng.launches, eng.model_calls = counts
-        graph = torch.cuda.CUDAGraph()
-        lib = _native.load()
-        cap_stream = torch.cuda.Stream(device=self.device)
-        cap = C.c_void_p(cap_stream.cuda_stream)
-        if self.l2_persist:   # configured before capture begins; the window then rides on every captured kernel node
-            nbytes = self.y.numel() * 4
-            if lib.lp_l2_persist_set(C.c_void_p(self.y.data_ptr()), nbytes, cap) == 0:
-                self.l2_window = nbytes
-        with torch.cuda.graph(graph, stream=cap_stream):
-            self._body(pm, dims, plan)
-        if self.l2_window:
-            lib.lp_l2_persist_clear(cap)
-        self.graph, self.draws = graph, plan.used
-        self.launches, self.model_calls = eng.launches - counts[0], eng.model_calls - counts[1]
-        eng.launches, eng.model_calls = counts
+        st = self.sched.steps[i]
+        coef = (st.sigma_next - st.sigma) / st.sigma
+        last = i + 1 == len(self.sched.steps)
+        plan.used = self.draws_before[i]
+        out = self.out if (want_out or not self.fused_euler) else None
+        eng._launch_sequence(self.x, self.y, self.noise, self.mask, self._dims, self.tables[i], self.t_model[i],
+                             self.sigma[i], self.c, out, self.active[i], plan, False, self.model_options, self.seed,
+                             None, self.rng_state.data_ptr(), euler_coef=coef if self.fused_euler else None,
+                             skip_prologue=(self.fused_euler and i > 0) or (i == 0 and self.first_replace_noop),
+                             next_table=self.tables[i + 1] if (self.fused_euler and not last) else None)
+        if not self.fused_euler:
+            self.x.add_(self.x - self.out, alpha=coef)
 
-    def run(self, latent_image: torch.Tensor, noise: torch.Tensor, mask, x_out: Optional[torch.Tensor] = None):
+    def _body(self, plan, want_out):
+        if not self.external_init:
+            self._init_state()
+        for i in range(len(self.sched.steps)):
+            self._step(i, plan, want_out)
+
+    def _relative_plan(self):
+        return self._plan_cls(self.engine.rng, self.x, 1).relative()
+
+    def _capture(self, fn, warm: bool):
+        """Capture `fn(plan)` into a CUDA graph.  warm=True first runs it once on a side stream (lazy
+        initialisation of whatever the model uses); the node path passes warm=False because the same body has
+        already run eagerly as the previous job."""
+        eng = self.engine
+        counts = (eng.launches, eng.model_calls, eng.substeps_done)
+        timer, eng.kernel_timer = eng.kernel_timer, None
+        try:
+            if warm:
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    fn(self._relative_plan())
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                eng.launches, eng.model_calls, eng.substeps_done = counts
+            graph = torch.cuda.CUDAGraph()
+            lib = _native.load()
+            cap_stream = torch.cuda.Stream(device=self.device)
+            cap = C.c_void_p(cap_stream.cuda_stream)
+            if self.l2_persist:   # configured before capture begins; the window then rides on every captured kernel node
+                nbytes = self.y.numel() * 4
+                if lib.lp_l2_persist_set(C.c_void_p(self.y.data_ptr()), nbytes, cap) == 0:
+                    self.l2_window = nbytes
+            cap_stream.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.graph(graph, stream=cap_stream):
+                fn(self._relative_plan())
+            if self.l2_window:
+                lib.lp_l2_persist_clear(cap)
+        finally:
+            eng.kernel_timer = timer
+        stats = (eng.launches - counts[0], eng.model_calls - counts[1])
+        eng.launches, eng.model_calls, eng.substeps_done = counts
+        self.captures += 1
+        return graph, stats
+
+    def _graph_for(self, key, fn, warm):
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = self._capture(fn, warm)
+        return g
+
+    # ---- one job ---------------------------------------------------------------------------------
+    def load_inputs(self, latent_image: torch.Tensor, noise: torch.Tensor, mask, x_init=None):
+        """Copies of the request's own inputs into the static buffers (H2D when they are host tensors)."""
         import numpy as np
         from .engine import PackedMask, pack_mask
-        eng = self.engine
         self.y.copy_(latent_image, non_blocking=True)
         self.noise.copy_(noise, non_blocking=True)
+        if x_init is not None:
+            self.x.copy_(x_init, non_blocking=True)
         pm = mask if isinstance(mask, PackedMask) else pack_mask(mask, self.x)
         if self.mask is None or self.mask.data.shape != pm.data.shape or (
                 self.mask.row_stride, self.mask.channel_stride) != (pm.row_stride, pm.channel_stride):
             self.mask = PackedMask(torch.empty_like(pm.data), pm.row_stride, pm.channel_stride)
-            self.graph = None
+            self._graphs = {}
         self.mask.data.copy_(pm.data, non_blocking=True)
-        if self.graph is None:
-            self._capture(self.mask)
-        plan = self._plan_cls(eng.rng, self.x, 1)
-        self.rng_state.copy_(torch.from_numpy(plan.state_words().view(np.int64)))
-        self.graph.replay()
-        plan.consume(self.draws)
-        plan.finish()
-        eng.launches += self.launches
-        eng.model_calls += self.model_calls
-        eng.substeps_done += self.sched.substeps
-        if x_out is not None:
-            x_out.copy_(self.x, non_blocking=True)
-            return x_out
-        return self.x.clone()
+        B = self.shape[0]
+        self._dims = _native.Dims(B, self.x.numel() // B, int(np.prod(self.shape[2:])), self.mask.row_stride,
+                                  self.mask.channel_stride)
+
+    def run(self, latent_image: torch.Tensor, noise: torch.Tensor, mask, x_out: Optional[torch.Tensor] = None,
+            x_init: Optional[torch.Tensor] = None, callback=None, mode: Optional[str] = None, warm: bool = True):
+        """callback(i, denoised, x, total_steps) is called on the host after outer step i has been ENQUEUED
+        (it sees device tensors in stream order; a callback that only counts steps never synchronises)."""
+        import numpy as np
+        eng = self.engine
+        if self.external_init != (x_init is not None):
+            raise ValueError("x_init must be given exactly when the job was built with external_init=True")
+        if mode is None:
+            mode = "steps" if callback is not None else "job"
+        with torch.cuda.device(self.device):
+            before = (eng.launches, eng.model_calls)
+            self.load_inputs(latent_image, noise, mask, x_init)
+            plan = self._plan_cls(eng.rng, self.x, 1)
+            self.rng_state.copy_(torch.from_numpy(plan.state_words().view(np.int64)))
+            n_steps = len(self.sched.steps)
+            want_out = callback is not None
+            if mode == "job" and not want_out:
+                graph, stats = self._graph_for(("job", False), lambda p: self._body(p, False), warm)
+                graph.replay()
+                eng.launches += stats[0]
+                eng.model_calls += stats[1]
+            elif mode in ("steps", "job"):
+                if not self.external_init:
+                    self._init_state()
+                for i in range(n_steps):
+                    graph, stats = self._graph_for(("step", i, want_out), lambda p, i=i: self._step(i, p, want_out), warm)
+                    graph.replay()
+                    eng.launches += stats[0]
+                    eng.model_calls += stats[1]
+                    if callback is not None:
+                        callback(i, self.out, self.x, n_steps)
+            elif mode == "eager":
+                rel = self._relative_plan()
+                if not self.external_init:
+                    self._init_state()
+                for i in range(n_steps):
+                    self._step(i, rel, want_out)
+                    if callback is not None:
+                        callback(i, self.out, self.x, n_steps)
+            else:
+                raise ValueError(f"unknown mode {mode!r}")
+            plan.consume(self.draws)
+            plan.finish()
+            eng.substeps_done += self.sched.substeps
+            self.launches, self.model_calls = eng.launches - before[0], eng.model_calls - before[1]
+            if x_out is not None:
+                x_out.copy_(self.x, non_blocking=True)
+                return x_out
+            return self.x.clone()

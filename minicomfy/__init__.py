@@ -428,18 +428,28 @@ def common_ksampler(model, seed, steps, cfg, sampler_name, scheduler, positive, 
     else:
         noise = prepare_noise(latent_image, seed, latent.get("batch_index"))
     noise_mask = latent.get("noise_mask")
+    # like ComfyUI: there is always a callback (progress bar; a preview only when a previewer is configured)
+    callback = sys.modules["latent_preview"].prepare_callback(model, steps)
     samples = sample(model, noise, steps, cfg, sampler_name, scheduler, positive, negative, latent_image,
                      denoise=denoise, disable_noise=disable_noise, start_step=start_step, last_step=last_step,
-                     force_full_denoise=force_full_denoise, noise_mask=noise_mask, seed=seed)
+                     force_full_denoise=force_full_denoise, noise_mask=noise_mask, callback=callback,
+                     disable_pbar=not PROGRESS_BAR_ENABLED, seed=seed)
     out = latent.copy()
     out["samples"] = samples
     return (out,)
 
 
+PROGRESS = {"calls": 0, "last": None}
+
+
 def prepare_callback(model, steps, x0_output_dict=None):
+    """ComfyUI's latent_preview.prepare_callback with no previewer configured: keeps the latest x0 for the
+    custom-sampler nodes and advances the progress bar; never reads device memory."""
     def callback(step, x0, x, total_steps):
         if x0_output_dict is not None:
             x0_output_dict["x0"] = x0
+        PROGRESS["calls"] += 1
+        PROGRESS["last"] = (step + 1, total_steps)
     return callback
 
 

@@ -211,24 +211,199 @@ def test_flux_type_model_runs_on_the_flow_schedule(cuda_device):
     assert max_rel(out["samples"], want) <= 1e-4
 
 
-def test_node_path_with_graph_replay_equals_eager(cuda_device):
-    """model_options["lanpaint_b200"] = {"cuda_graph": True}: the whole outer step, including the guider's
-    cond/uncond evaluations, is captured once per sub-step count and replayed; results must not change."""
+def _ksampler_run(N, dev, y, noise_mask, opts=None, seed=11, cfg=5.0, sampler="euler", steps=20, n=5,
+                  patcher=None, conds=(0.3, -0.2)):
+    if patcher is None:
+        patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+    if opts is not None:
+        patcher.model_options["lanpaint_b200"] = opts
+    (out,) = N.LanPaint_KSampler().sample(patcher, seed, steps, cfg, sampler, "karras", conds[0], conds[1],
+                                          {"samples": y, "noise_mask": noise_mask}, 1.0, n, "Image First", "",
+                                          N.IMAGE_MODE)
+    return out["samples"], patcher
+
+
+def test_node_default_is_graph_replay_and_matches_oracle(cuda_device):
+    """The node path with NO options (what a workflow gets): Euler is run by the host-owned fused loop; the first
+    job of a configuration launches eagerly, the second captures one CUDA graph per outer step (ComfyUI always
+    passes a progress callback), later ones only replay.  Every one of them must equal the oracle's restatement
+    of the reference run with the same seed (rng="torch": the reference's own randn stream), and each other bit
+    for bit."""
     minicomfy.install()
     from lanpaint_b200 import comfy_nodes as N
+    N._ENGINES.clear()
     dev = cuda_device
     g = torch.Generator().manual_seed(6)
+    y = torch.randn(2, 4, 32, 32, generator=g)
+    noise_mask = (torch.rand(2, 1, 32, 32, generator=g) < 0.5).float()
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+    outs, modes = [], []
+    calls0 = minicomfy.PROGRESS["calls"]
+    for _ in range(4):
+        o, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher)
+        outs.append(o)
+        modes.append(N.LAST_RUN["mode"])
+        eng = N.LAST_ENGINE["engine"]
+        assert eng.model_calls == 73 and eng.substeps_done == 53 and eng.rng == "torch"
+    assert modes == ["eager", "steps", "steps", "steps"], modes
+    assert minicomfy.PROGRESS["calls"] - calls0 == 4 * 20 and minicomfy.PROGRESS["last"] == (20, 20)
+    assert N.LAST_RUN["job"].captures == 20
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    noise = minicomfy.prepare_noise(y, 11)        # re-seeds every generator exactly like the node call did
+    model = _OracleGuider(0.3, -0.2, 5.0, 5.0)
+    want = O.euler_inpaint(model, y.to(dev), noise.to(dev), noise_mask.expand(2, 4, 32, 32).to(dev),
+                           O.karras_sigmas(20).to(dev), O.Hyper(n_steps=5, min_step_frac=1.0), max_denoise=True)
+    assert max_rel(outs[0], want) <= 1e-4
+    # the un-fused route (k-diffusion's own loop around the per-sigma wrapper, plain launches) agrees too
+    plain, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False, "fused_sampler": False})
+    assert N.LAST_RUN["fused"] is False
+    assert max_rel(outs[0], plain) <= 2e-5
+
+
+def test_node_cache_is_keyed_on_what_a_graph_bakes_in(cuda_device):
+    """A different guidance scale, prompt object or seed must never replay a stale graph."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    N._ENGINES.clear()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(8)
     y = torch.randn(1, 4, 32, 32, generator=g)
     noise_mask = (torch.rand(1, 1, 32, 32, generator=g) < 0.5).float()
-    res = {}
-    for graph in (False, True):
-        patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
-        patcher.model_options["lanpaint_b200"] = {"cuda_graph": graph}
-        (out,) = N.LanPaint_KSampler().sample(patcher, 11, 20, 5.0, "euler", "karras", 0.3, -0.2,
-                                              {"samples": y, "noise_mask": noise_mask}, 1.0, 5, "Image First", "",
-                                              N.IMAGE_MODE)
-        res[graph] = (out["samples"], N.LAST_ENGINE["engine"])
-    assert torch.equal(res[True][0], res[False][0])
-    eng = res[True][1]
-    assert len([v for v in eng._graphs.values() if v]) == 6       # sub-step counts 5,4,3,2,1,0 of karras-20 x N=5
-    assert eng.model_calls == 73 and eng.substeps_done == 53
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+    for _ in range(3):   # cfg 5 is now graph-replayed
+        a5, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, steps=8, n=3)
+    assert N.LAST_RUN["mode"] == "steps"
+    a7, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, steps=8, n=3, cfg=7.0)
+    assert N.LAST_RUN["mode"] == "eager"
+    ref7, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False}, steps=8, n=3, cfg=7.0)
+    assert torch.equal(a7, ref7) and not torch.equal(a7, a5)
+    # another seed replays the same graphs with a fresh noise image and a fresh randn stream
+    b5, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, steps=8, n=3, seed=12)
+    assert N.LAST_RUN["mode"] == "steps"
+    refb, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False}, steps=8, n=3, seed=12)
+    assert torch.equal(b5, refb) and not torch.equal(b5, a5)
+    # a float conditioning of equal value is the same prompt for minicomfy; a different value is not
+    c5, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, steps=8, n=3, conds=(0.5, -0.2))
+    refc, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False}, steps=8, n=3, conds=(0.5, -0.2))
+    assert torch.equal(c5, refc)
+
+
+def test_whole_job_graph_when_nobody_wants_a_callback(cuda_device):
+    """guider.sample(...) without a callback (custom hosts): the fused loop is ONE graph for the whole job."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    N._ENGINES.clear()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(3)
+    y = torch.randn(1, 4, 32, 32, generator=g)
+    noise = torch.randn(1, 4, 32, 32, generator=g)
+    noise_mask = (torch.rand(1, 1, 32, 32, generator=g) < 0.5).float()
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+    N._set_hyper(patcher, num_steps=4, cfg=4.0, prompt_mode="Image First")
+    sig = minicomfy.get_sigmas_karras(10, 0.0292, 14.6146)
+    outs, modes = [], []
+    for _ in range(3):
+        guider = minicomfy.CFGGuider(patcher)
+        guider.set_conds(0.3, -0.2)
+        guider.set_cfg(4.0)
+        torch.manual_seed(21)
+        with N.override_sample_function():
+            outs.append(guider.sample(noise, y, minicomfy.ksampler("euler"), sig, denoise_mask=noise_mask, seed=1))
+        modes.append(N.LAST_RUN["mode"])
+    assert modes == ["eager", "job", "job"]
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert N.LAST_RUN["job"].captures == 1
+
+
+def test_other_samplers_replay_one_graph_per_outer_step(cuda_device):
+    """heun (any sampler that is not plain Euler) goes through k-diffusion's own loop; the per-sigma wrapper
+    replays one CUDA graph per outer step, cached across sample() calls.  Same results as plain launches."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    N._ENGINES.clear()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(1, 4, 32, 32, generator=g)
+    noise_mask = (torch.rand(1, 1, 32, 32, generator=g) < 0.5).float()
+    plain, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False}, sampler="heun", steps=10, n=3)
+    calls = N.LAST_ENGINE["engine"].model_calls
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+    for k in range(3):
+        got, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, sampler="heun", steps=10, n=3)
+        assert N.LAST_RUN["fused"] is False
+        assert torch.equal(got, plain), k
+        assert N.LAST_ENGINE["engine"].model_calls == calls
+    eng = N.LAST_ENGINE["engine"]
+    assert len([v for v in eng._graphs.values() if v]) >= 3
+
+
+def test_av_flat_pack_through_the_node_layer(cuda_device, monkeypatch):
+    """MiniMax-H3 AV pack entered through the nodes (PackedMask from the per-sigma wrapper, audio rows on their
+    own schedule) == the engine seam driven with tensor masks and the same per-step arguments."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    from lanpaint_b200.engine import LanPaint
+    from lanpaint_b200.schedule import times_from_sigma
+    N._ENGINES.clear()
+    dev = cuda_device
+
+    def shift_sigma(s, sv, sa):       # stand-ins for comfy.ldm.minimax.model.time_shift_sigma / _slope
+        return sa * s / (sv + (sa - sv) * s)
+
+    def shift_slope(s, sv, sa):
+        return sa * sv / (sv + (sa - sv) * s) ** 2
+    monkeypatch.setattr(N, "time_shift_sigma", shift_sigma)
+    monkeypatch.setattr(N, "time_shift_slope", shift_slope)
+
+    def net(x, sigma, cond):
+        return 0.7 * x + 0.1 * torch.tanh(x) + cond
+    net.sigma_shift_video, net.sigma_shift_audio = 3.0, 1.5
+    g = torch.Generator().manual_seed(12)
+    n_video, n_audio = 96, 32
+    y = torch.randn(1, 8, n_video + n_audio, generator=g)
+    noise = torch.randn(1, 8, n_video + n_audio, generator=g)
+    noise_mask = (torch.rand(1, 8, n_video + n_audio, generator=g) < 0.5).float()
+    sig = torch.tensor([0.95, 0.8, 0.6, 0.4, 0.2, 0.0])
+
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(net, model_type=minicomfy.ModelType.FLOW), dev)
+    N._set_hyper(patcher, num_steps=3, cfg=1.0, prompt_mode="Image First")
+    guider = minicomfy.CFGGuider(patcher)
+    guider.set_conds(0.3, -0.2)
+    guider.set_cfg(1.0)
+    torch.manual_seed(4)
+    with N.override_sample_function():
+        got = type(guider).outer_sample(guider, noise, y, minicomfy.ksampler("euler"), sig, denoise_mask=noise_mask,
+                                        seed=2, latent_shapes=[(1, n_video), (1, n_audio)])
+    assert N.LAST_RUN["fused"] is False and torch.isfinite(got).all()
+
+    # the same run against the engine seam: tensor mask, explicit audio arguments per outer step
+    class Guider:
+        inner_model = None
+
+        def __init__(self):
+            self.inner_model = self
+            self.model_sampling = minicomfy.ModelSamplingCONST()
+
+        def __call__(self, x, t, model_options=None, seed=None):
+            return net(x, t, 0.3)
+    eng = LanPaint(Guider(), 3, 15.0, 5.0, 1.0, 0.2, IS_FLOW=True, MinStepFrac=1.0)
+    torch.manual_seed(4)
+    yd, nd = y.to(dev), noise.to(dev)
+    x = Guider().model_sampling.noise_scaling(sig[0].to(dev), nd, yd)
+    ind = torch.zeros_like(x)
+    ind[..., n_video:] = 1.0
+    known = (1.0 - noise_mask).to(dev)
+    host = [float(v) for v in sig]
+    for i in range(len(host) - 1):
+        s = torch.full((1,), host[i])
+        times = times_from_sigma(s, True)
+        n_eff = N.effective_inner_steps(3, host, host[i], float((1 - times[1]).mean()), 1, 1.0)
+        fa = shift_sigma(times[2], 3.0, 1.5)
+        abt_a = (1 - fa) ** 2 / ((1 - fa) ** 2 + fa ** 2)
+        c = float(fa) / (host[i] * float(shift_slope(times[2], 3.0, 1.5))) if host[i] > 1e-4 else 1.0
+        den = eng(x, yd, nd, s, known, times, {}, 2, n_steps=n_eff, current_times_audio=(fa / (1 - fa), abt_a, fa),
+                  audio_indicator=ind, audio_correction=(1.0 - ind) + c * ind)
+        x = x + (x - den) / host[i] * (host[i + 1] - host[i])
+    want = Guider().model_sampling.inverse_noise_scaling(sig[-1].to(dev), x)
+    assert max_rel(got, want) <= 1e-5
