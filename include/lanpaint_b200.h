@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 3
+#define LP_ABI_VERSION 4
 #define LP_TABLE_STRIDE 32 /* floats per table row (one 128-byte line), layout below */
 
 typedef void* lp_stream_t; /* a cudaStream_t / CUstream */
@@ -111,14 +111,39 @@ typedef struct lp_rng {
                             replayed with a fresh stream position) */
 } lp_rng;
 
+/* Element type of the model's output tensors ("heads").  State, clean latent, noise and all arithmetic are
+ * fp32 like the reference's (its autocast(float32) wrappers, lanpaint.py:201,239); a network that returns
+ * bf16 / fp16 predictions is read as is and widened in registers -- the same values the reference gets from
+ * type promotion when it subtracts an fp32 x_t from them (lanpaint.py:182-184) -- instead of paying a
+ * separate .float() pass (6 B/element read + 8 B/element written per head pair). */
+typedef enum lp_dtype { LP_DTYPE_F32 = 0, LP_DTYPE_BF16 = 1, LP_DTYPE_F16 = 2 } lp_dtype;
+
+/* The model's prediction(s) for one call, as the kernels consume them (src/LanPaint/lanpaint.py:34-43,
+ * 159-171; src/LanPaint/nodes.py:161-175):
+ *   combine == 0   a = x0, b = x0_BIG (NULL or == a: the two heads alias)
+ *   combine != 0   a = cond, b = uncond (raw network outputs); the kernel forms
+ *                  x0 = b + (a - b)*cfg and x0_BIG = b + (a - b)*cfg_big in registers with the eager
+ *                  sub/mul/add roundings (requires dtype == LP_DTYPE_F32 so that they ARE the eager roundings) */
+typedef struct lp_heads {
+  const void* a;
+  const void* b;
+  int32_t dtype;   /* lp_dtype of a and b */
+  int32_t combine;
+  float cfg, cfg_big;
+} lp_heads;
+
 /* ---- library ---------------------------------------------------------- */
 int lp_abi_version(void);
 const char* lp_status_string(int status);
 int lp_last_cuda_error(void); /* cudaError_t of the last failed launch on this thread */
-/* Process-wide switches (also read once from the environment: LANPAINT_B200_PDL, LANPAINT_B200_TMA):
- *   "pdl" 1|0  programmatic dependent launch on every kernel (default 1)
- *   "tma" 1|0  use the TMA-staged persistent variant of the fused sub-step (cp.async.bulk + mbarrier ring) when
- *              eligible: philox stream, >= 2^20 elements, spatial a multiple of 16 (default 1) */
+/* Process-wide switches (also read once from the environment: LANPAINT_B200_PDL, LANPAINT_B200_TMA,
+ * LANPAINT_B200_TMA_MIN):
+ *   "pdl" 1|0      programmatic dependent launch on every kernel (default 1)
+ *   "tma" 1|0      use the TMA-staged persistent variants (cp.async.bulk + mbarrier ring) of the fused sub-step
+ *                  (philox and torch streams) and of the step-boundary kernel when eligible: spatial a multiple
+ *                  of 16, no side outputs, no row split (default 1; 2.. select alternative tile geometries of
+ *                  the philox kernel for measurement)
+ *   "tma_min"      smallest launch, in elements, that takes a TMA-staged variant (default 2^18) */
 int lp_set_option(const char* name, int value);
 
 /* Host-only self test of the index arithmetic the kernels rely on (the multiply-shift division that
@@ -191,6 +216,12 @@ int lp_substep_f32(float* x_model, const float* x0, const float* x0_big, const f
                    const float* table, const lp_dims* dims, const lp_rng* rng, int flags,
                    lp_stream_t stream);
 
+/* The general form of lp_substep_f32: heads of any lp_dtype, optionally the two classifier-free-guidance
+ * combines folded in (lp_heads).  lp_substep_f32 / lp_substep_cfg_f32 are this call with fp32 heads. */
+int lp_substep(float* x_model, const lp_heads* heads, const float* y, const uint8_t* mask, float* c_state,
+               float* x_copy, float* x0e_out, const float* table, const lp_dims* dims, const lp_rng* rng,
+               int flags, lp_stream_t stream);
+
 /* lp_substep_f32 with the two classifier-free-guidance combines folded in (replaces the
  * two cfg_function calls of sampling_function_LanPaint, src/LanPaint/nodes.py:175): the caller passes the
  * network's raw cond / uncond x0 predictions and the two scales,
@@ -232,6 +263,16 @@ int lp_step_boundary_f32(const float* model_out, const float* y, const float* no
                          float* x_inout, float* out, float euler_coef, const float* next_table,
                          const lp_dims* dims, lp_stream_t stream);
 
+/* The general boundary of an outer step, everything after its last model call in ONE pass
+ * (lanpaint.py:151-157, k-diffusion sample_euler, lanpaint.py:85-94 of the next step):
+ *   d   = model_out->combine ? b + (a - b)*cfg : a                      (heads of any lp_dtype)
+ *   out = mask ? y : d                                                  written when out != NULL
+ *   x   = x + (x - out)*euler_coef                                      when x_inout != NULL
+ *   x   = mask ? rep_noise*noise + rep_y*y : x  (row of next_table)     when next_table != NULL (needs noise, x_inout)
+ * lp_epilogue_f32, lp_epilogue_euler_f32, lp_step_boundary_f32 and lp_epilogue_cfg_f32 are special cases. */
+int lp_boundary(const lp_heads* model_out, const float* y, const float* noise, const uint8_t* mask, float* x_inout,
+                float* out, float euler_coef, const float* next_table, const lp_dims* dims, lp_stream_t stream);
+
 /* Final denoise of an outer step straight from raw cond / uncond predictions:
  *   out = mask ? y : uncond + (cond - uncond)*cfg ;  if x_inout != NULL: x = x + (x - out)*euler_coef. */
 int lp_epilogue_cfg_f32(const float* cond, const float* uncond, float cfg, const float* y, const uint8_t* mask,
@@ -256,6 +297,9 @@ int lp_fill_normal_f32(float* out, int64_t n, const lp_rng* rng, lp_stream_t str
  *   h0 = a0*x + b0*tanh(x) + c0 ;  h1 = a1*x + c1     coef = {a0,b0,c0,a1,c1} */
 int lp_synth_denoiser_f32(const float* x, float* h0, float* h1, int64_t n, const float* coef5_host,
                           lp_stream_t stream);
+/* Same, heads written in `dtype` (a network that computes in bf16 returns bf16 predictions). */
+int lp_synth_denoiser(const float* x, void* h0, void* h1, int dtype, int64_t n, const float* coef5_host,
+                      lp_stream_t stream);
 
 /* L2 residency for the operands every sub-step re-reads (the clean latent y and the mask: 4 + 1/C of the
  * 28 + 1/C bytes per element).  B200 has 126 MB of L2; pinning y (and the mask that follows it in the same

@@ -12,17 +12,19 @@ from typing import Optional
 _LIB_PATH = os.environ.get("LANPAINT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
                                                                "liblanpaint_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 TABLE_STRIDE = 32
 
 RNG_TAPE, RNG_PHILOX, RNG_TORCH = 0, 1, 2
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 T_INVS = 2  # LP_T_INVS
 SUBSTEP_FIRST, SUBSTEP_FUSE_NEXT, SUBSTEP_STORE_C, SUBSTEP_MERGE_NOISE = 1, 2, 4, 8
 
 # every symbol include/lanpaint_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = (
     "lp_abi_version", "lp_status_string", "lp_last_cuda_error", "lp_set_option", "lp_selftest_index_math", "lp_build_coef_table", "lp_build_coef_table_dt",
-    "lp_torch_randn_geometry", "lp_pack_mask_f32", "lp_prologue_f32", "lp_substep_f32", "lp_substep_cfg_f32", "lp_advance_f32",
+    "lp_torch_randn_geometry", "lp_pack_mask_f32", "lp_prologue_f32", "lp_substep", "lp_substep_f32", "lp_substep_cfg_f32", "lp_advance_f32",
+    "lp_boundary", "lp_synth_denoiser",
     "lp_epilogue_f32", "lp_epilogue_euler_f32", "lp_step_boundary_f32", "lp_epilogue_cfg_f32", "lp_stop_stats_f32", "lp_fill_normal_f32", "lp_synth_denoiser_f32", "lp_l2_persist_capacity", "lp_l2_persist_set", "lp_l2_persist_clear", "lp_l2_flush",
 )
 
@@ -34,6 +36,12 @@ class NativeError(RuntimeError):
 class Hyper(C.Structure):
     _fields_ = [("step_size", C.c_double), ("lam", C.c_double), ("beta", C.c_double),
                 ("min_step_frac", C.c_double), ("flow", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Heads(C.Structure):
+    """lp_heads: the model's prediction(s) of one call (x0 / x0_BIG, or raw cond / uncond with combine=1)."""
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("dtype", C.c_int32), ("combine", C.c_int32),
+                ("cfg", C.c_float), ("cfg_big", C.c_float)]
 
 
 class Dims(C.Structure):
@@ -84,6 +92,12 @@ def load() -> C.CDLL:
     lib.lp_pack_mask_f32.argtypes = [p, p, i64, i32, p]
     lib.lp_prologue_f32.restype = i32
     lib.lp_prologue_f32.argtypes = [p, p, p, p, p, p, p, C.POINTER(Dims), p]
+    lib.lp_substep.restype = i32
+    lib.lp_substep.argtypes = [p, C.POINTER(Heads), p, p, p, p, p, p, C.POINTER(Dims), C.POINTER(Rng), i32, p]
+    lib.lp_boundary.restype = i32
+    lib.lp_boundary.argtypes = [C.POINTER(Heads), p, p, p, p, p, C.c_float, p, C.POINTER(Dims), p]
+    lib.lp_synth_denoiser.restype = i32
+    lib.lp_synth_denoiser.argtypes = [p, p, p, i32, i64, p, p]
     lib.lp_substep_f32.restype = i32
     lib.lp_substep_f32.argtypes = [p, p, p, p, p, p, p, p, p, C.POINTER(Dims), C.POINTER(Rng), i32, p]
     lib.lp_substep_cfg_f32.restype = i32

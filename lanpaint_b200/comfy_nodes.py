@@ -335,6 +335,8 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
 
     def sample(self, model_wrap, sigmas, extra_args, callback, noise, latent_image=None, denoise_mask=None,
                disable_pbar=False):
+        # NB: while the patch is active this function is installed on comfy.samplers.KSAMPLER itself, so `self`
+        # is ComfyUI's class, not this subclass: helpers are reached through the class, never through `self`
         extra_args["denoise_mask"] = denoise_mask
         LAST_RUN.update(mode=None, fused=False, job=None, events=None)
         model_k = KSamplerX0Inpaint(model_wrap, sigmas)
@@ -393,8 +395,8 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
             timing[0].record()
 
         samples = None
-        if opts.get("fused_sampler", True) and self._fused_euler_ok(model_k, denoise_mask, model_options, engine):
-            samples = self._fused_euler(model_k, entry, engine, x_init, latent_image, denoise_mask, model_options,
+        if opts.get("fused_sampler", True) and KSAMPLER._fused_euler_ok(self, model_k, denoise_mask, model_options, engine):
+            samples = KSAMPLER._fused_euler(self, model_k, entry, engine, x_init, latent_image, denoise_mask, model_options,
                                         extra_args.get("seed"), is_flux or is_flow, early_stop, callback, total_steps,
                                         use_graph, opts)
         if samples is None:

@@ -473,16 +473,14 @@ class LanPaint:
             first = i == 0
             has_next = i + 1 < active
             self.model_calls += 1
-            pair = None
             if stopper is None or first:
                 heads = self.inner_model(xm, t_model, model_options=model_options, seed=seed)
-                if isinstance(heads, CfgPair) and stopper is None:
-                    pair = heads
-                    x0, x0b = _as_operand(pair.cond, xm), _as_operand(pair.uncond, xm)
+                if isinstance(heads, CfgPair) and stopper is None and heads.cond.dtype == torch.float32 \
+                        and heads.uncond.dtype == torch.float32:
+                    hd, keep = _heads(heads.cond, heads.uncond, xm, True, heads.cfg, heads.cfg_big)
                 else:
                     h0, h1 = self.unpack_model_output(heads)
-                    x0 = _as_operand(h0, xm)
-                    x0b = x0 if h1 is h0 else _as_operand(h1, xm)
+                    hd, keep = _heads(h0, h1, xm)
             if stopper is None:
                 # fused: post-model half of sub-step i + pre-model half of sub-step i+1
                 flags = (F.SUBSTEP_FIRST if first else 0) | (F.SUBSTEP_FUSE_NEXT if has_next else 0)
@@ -491,18 +489,13 @@ class LanPaint:
                     flags |= F.SUBSTEP_MERGE_NOISE
                 r = plan.rng_struct(2 if (has_next and not merge) else 1, rng_state)
                 ev = self._event_pair(flags) if self.kernel_timer is not None else None
-                if pair is None:
-                    rc = lib.lp_substep_f32(_P(xm.data_ptr()), _P(x0.data_ptr()), _P(x0b.data_ptr()),
-                                            _P(y.data_ptr()), _P(pm.data.data_ptr()), _P(cbuf.data_ptr()), None,
-                                            None, _P(tab.data_ptr()), C.byref(dims), C.byref(r), flags, stream)
-                else:  # both CFG combines happen inside the kernel
-                    rc = lib.lp_substep_cfg_f32(_P(xm.data_ptr()), _P(x0.data_ptr()), _P(x0b.data_ptr()),
-                                                C.c_float(pair.cfg), C.c_float(pair.cfg_big), _P(y.data_ptr()),
-                                                _P(pm.data.data_ptr()), _P(cbuf.data_ptr()), None, None,
-                                                _P(tab.data_ptr()), C.byref(dims), C.byref(r), flags, stream)
+                # heads of any dtype; with a CfgPair both CFG combines happen inside the kernel
+                rc = lib.lp_substep(_P(xm.data_ptr()), C.byref(hd), _P(y.data_ptr()), _P(pm.data.data_ptr()),
+                                    _P(cbuf.data_ptr()), None, None, _P(tab.data_ptr()), C.byref(dims), C.byref(r),
+                                    flags, stream)
                 if ev is not None:
                     ev[1].record()
-                _native.check(rc, "lp_substep_f32")
+                _native.check(rc, "lp_substep")
                 self.launches += 1
                 done += 1
                 continue
@@ -520,15 +513,14 @@ class LanPaint:
                 self.launches += 1
                 heads = self.inner_model(xm, t_model, model_options=model_options, seed=seed)
                 h0, h1 = self.unpack_model_output(heads)
-                x0 = _as_operand(h0, xm)
-                x0b = x0 if h1 is h0 else _as_operand(h1, xm)
+                hd, keep = _heads(h0, h1, xm)
             flags = (F.SUBSTEP_FIRST if first else 0) | F.SUBSTEP_STORE_C
             x0e = stopper.next_x0e_buffer(xm)
             r = plan.rng_struct(1, rng_state)
-            rc = lib.lp_substep_f32(_P(xm.data_ptr()), _P(x0.data_ptr()), _P(x0b.data_ptr()), _P(y.data_ptr()),
-                                    _P(pm.data.data_ptr()), _P(cbuf.data_ptr()), None, _P(x0e.data_ptr()),
-                                    _P(tab.data_ptr()), C.byref(dims), C.byref(r), flags, stream)
-            _native.check(rc, "lp_substep_f32")
+            rc = lib.lp_substep(_P(xm.data_ptr()), C.byref(hd), _P(y.data_ptr()), _P(pm.data.data_ptr()),
+                                _P(cbuf.data_ptr()), None, _P(x0e.data_ptr()), _P(tab.data_ptr()), C.byref(dims),
+                                C.byref(r), flags, stream)
+            _native.check(rc, "lp_substep")
             self.launches += 1
             done += 1
             inv_s = tab[:, _native.T_INVS].reshape((-1,) + (1,) * (xm.ndim - 1))
@@ -551,37 +543,22 @@ class LanPaint:
             if stop:
                 break
 
-        # final denoise + known-region paste (lanpaint.py:151-157)
+        # final denoise + known-region paste (lanpaint.py:151-157) [+ Euler update + next replace step when the host
+        # owns the sampler loop]: one lp_boundary launch, CFG combine folded in when the guider handed raw predictions
         out_heads = self.inner_model(xm, sigma_dev, model_options=model_options, seed=seed)
         self.model_calls += 1
-        if isinstance(out_heads, CfgPair) and (next_table is not None or out is None):
-            out_heads = (out_heads.uncond + (out_heads.cond - out_heads.uncond) * out_heads.cfg,)
-        if isinstance(out_heads, CfgPair):
-            cd, uc = _as_operand(out_heads.cond, xm), _as_operand(out_heads.uncond, xm)
-            rc = lib.lp_epilogue_cfg_f32(_P(cd.data_ptr()), _P(uc.data_ptr()), C.c_float(out_heads.cfg),
-                                         _P(y.data_ptr()), _P(pm.data.data_ptr()),
-                                         _P(xm.data_ptr()) if euler_coef is not None else None, _P(out.data_ptr()),
-                                         C.c_float(euler_coef or 0.0), C.byref(dims), stream)
-            _native.check(rc, "lp_epilogue_cfg_f32")
-            self.launches += 1
-            return done
-        mo, _ = self.unpack_model_output(out_heads)
-        mo = _as_operand(mo, xm)
-        if next_table is not None and euler_coef is not None:
-            rc = lib.lp_step_boundary_f32(_P(mo.data_ptr()), _P(y.data_ptr()), _P(nz.data_ptr()),
-                                          _P(pm.data.data_ptr()), _P(xm.data_ptr()), _P(_ptr(out)),
-                                          C.c_float(euler_coef), _P(next_table.data_ptr()), C.byref(dims), stream)
-            _native.check(rc, "lp_step_boundary_f32")
-            self.launches += 1
-            return done
-        if euler_coef is None:
-            rc = lib.lp_epilogue_f32(_P(mo.data_ptr()), _P(y.data_ptr()), _P(pm.data.data_ptr()), _P(out.data_ptr()),
-                                     C.byref(dims), stream)
-        else:  # host-owned sampler loop: fold k-diffusion's Euler update of x into the same pass
-            rc = lib.lp_epilogue_euler_f32(_P(mo.data_ptr()), _P(y.data_ptr()), _P(pm.data.data_ptr()),
-                                           _P(xm.data_ptr()), _P(_ptr(out)), C.c_float(euler_coef),
-                                           C.byref(dims), stream)
-        _native.check(rc, "lp_epilogue_f32")
+        if isinstance(out_heads, CfgPair) and out_heads.cond.dtype == torch.float32 \
+                and out_heads.uncond.dtype == torch.float32:
+            hd, keep = _heads(out_heads.cond, out_heads.uncond, xm, True, out_heads.cfg, out_heads.cfg)
+        else:
+            mo, _ = self.unpack_model_output(out_heads)
+            hd, keep = _heads(mo, None, xm)
+        fused_next = next_table is not None and euler_coef is not None
+        rc = lib.lp_boundary(C.byref(hd), _P(y.data_ptr()), _P(nz.data_ptr()) if fused_next else None,
+                             _P(pm.data.data_ptr()), _P(xm.data_ptr()) if euler_coef is not None else None,
+                             _P(_ptr(out)), C.c_float(euler_coef or 0.0),
+                             _P(next_table.data_ptr()) if fused_next else None, C.byref(dims), stream)
+        _native.check(rc, "lp_boundary")
         self.launches += 1
         return done
 
@@ -899,14 +876,33 @@ def _repair_generator_after_failed_capture(dev: torch.device) -> None:
         pass
 
 
+_HEAD_DTYPES = {torch.float32: _native.DTYPE_F32, torch.bfloat16: _native.DTYPE_BF16, torch.float16: _native.DTYPE_F16}
+
+
 def _as_operand(t: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """A model output as a kernel operand: latent shape, contiguous, fp32 / bf16 / fp16 kept as is (the kernels
+    widen half-precision heads in registers, the values type promotion gives the reference at lanpaint.py:182-184);
+    anything else is converted to fp32."""
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"model returned {type(t).__name__}, expected a tensor")
     if t.shape != like.shape:
         t = t.expand(like.shape)
     if t.device != like.device:
         t = t.to(like.device)
-    return _f32c(t)
+    if t.dtype not in _HEAD_DTYPES:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _heads(a: torch.Tensor, b: Optional[torch.Tensor], like: torch.Tensor, combine: bool = False, cfg: float = 0.0,
+           cfg_big: float = 0.0):
+    """-> (lp_heads struct, tensors to keep alive).  a / b end up with one common dtype."""
+    a = _as_operand(a, like)
+    b = a if (b is None or b is a) else _as_operand(b, like)
+    if b.dtype != a.dtype or (combine and a.dtype != torch.float32):
+        a, b = a.float(), (a.float() if b is a else b.float())
+    h = _native.Heads(a.data_ptr(), b.data_ptr(), _HEAD_DTYPES[a.dtype], 1 if combine else 0, float(cfg), float(cfg_big))
+    return h, (a, b)
 
 
 def _probe_noise_scaling(sampling, sigma: float):

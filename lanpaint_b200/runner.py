@@ -54,12 +54,16 @@ class SynthDenoiser:
     `__call__(x, t, model_options=, seed=)`).  Output buffers are reused, which is
     what a CUDA-graph-captured network does too."""
 
-    def __init__(self, sampling=None, coef=(0.7, 0.1, 0.0, 0.6, -0.05), two_heads: bool = True):
+    def __init__(self, sampling=None, coef=(0.7, 0.1, 0.0, 0.6, -0.05), two_heads: bool = True,
+                 dtype: torch.dtype = torch.float32):
         self.inner_model = self
         self.model_sampling = sampling or VESampling()
         self.coef = tuple(float(c) for c in coef)
         self._coef_c = (C.c_float * 5)(*self.coef)
         self.two_heads = two_heads
+        self.dtype = dtype     # element type of the returned heads (a network computing in bf16 returns bf16)
+        self._dtype_code = {torch.float32: _native.DTYPE_F32, torch.bfloat16: _native.DTYPE_BF16,
+                            torch.float16: _native.DTYPE_F16}[dtype]
         self.calls = 0
         self._h0: Optional[torch.Tensor] = None
         self._h1: Optional[torch.Tensor] = None
@@ -71,13 +75,13 @@ class SynthDenoiser:
 
     def __call__(self, x, t, model_options=None, seed=None):
         if self._h0 is None or self._h0.shape != x.shape or self._h0.device != x.device:
-            self._h0 = torch.empty_like(x)
-            self._h1 = torch.empty_like(x) if self.two_heads else None
-        rc = self._lib.lp_synth_denoiser_f32(C.c_void_p(x.data_ptr()), C.c_void_p(self._h0.data_ptr()),
-                                             C.c_void_p(self._h1.data_ptr()) if self._h1 is not None else None,
-                                             x.numel(), self._coef_c,
-                                             C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
-        _native.check(rc, "lp_synth_denoiser_f32")
+            self._h0 = torch.empty_like(x, dtype=self.dtype)
+            self._h1 = torch.empty_like(x, dtype=self.dtype) if self.two_heads else None
+        rc = self._lib.lp_synth_denoiser(C.c_void_p(x.data_ptr()), C.c_void_p(self._h0.data_ptr()),
+                                         C.c_void_p(self._h1.data_ptr()) if self._h1 is not None else None,
+                                         self._dtype_code, x.numel(), self._coef_c,
+                                         C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+        _native.check(rc, "lp_synth_denoiser")
         self.calls += 1
         return (self._h0, self._h1) if self.two_heads else self._h0
 

@@ -715,6 +715,191 @@ def test_tma_staged_variant_is_bit_identical(cuda_device):
         lib.lp_set_option(b"tma", 1)   # the default
 
 
+def test_torch_stream_tma_variant_is_bit_identical(cuda_device):
+    """The seed-exact stream at HBM-bound sizes runs substep_torch_tma_kernel (producer warp + cp.async.bulk slots,
+    4 Philox subsequences per thread).  It must reproduce the LDG torch kernels bit for bit -- same randn stream,
+    same arithmetic -- on SDXL batches, on a Wan-sized video latent whose channel size is not a multiple of the
+    sub-tile (mask slices split at channel boundaries) and on a tensor that ends inside a plane."""
+    from lanpaint_b200 import _native
+    from lanpaint_b200.runner import SynthDenoiser, VESampling
+    lib = _native.load()
+    dev = cuda_device
+    res = {}
+    try:
+        for shape in ((24, 4, 128, 128), (1, 16, 21, 80, 45), (5, 4, 128, 128), (8, 4, 96, 112)):
+            x, y, noise, m = synth_inputs(shape, seed=33, device=dev)
+            sig = torch.full((shape[0],), 1.3)
+            times = tuple(O.times_from_sigma(sig, False))
+            for tma in (0, 1):
+                assert lib.lp_set_option(b"tma", tma) == 0
+                torch.manual_seed(23)
+                eng = _engine(SynthDenoiser(VESampling()), dict(n_steps=4), rng="torch", batched_replace="per_sample")
+                xx = x.clone()
+                out = eng(xx, y, noise, sig, m, times, None, 0, n_steps=4)
+                res[(shape, tma)] = (out, xx, torch.cuda.default_generators[dev.index or 0].get_offset())
+            assert torch.equal(res[(shape, 0)][0], res[(shape, 1)][0]), shape
+            assert torch.equal(res[(shape, 0)][1], res[(shape, 1)][1]), shape
+            assert res[(shape, 0)][2] == res[(shape, 1)][2]
+    finally:
+        lib.lp_set_option(b"tma", 1)
+
+
+@pytest.mark.parametrize("rng", ["philox", "torch"])
+def test_tma_variants_with_fused_cfg_combine(rng, cuda_device):
+    """cond / uncond fed straight to the TMA-staged kernels (>= 2^20 elements, lp_heads.combine) == the same run
+    with the LDG kernels == the combines materialised by torch."""
+    from lanpaint_b200 import _native
+    from lanpaint_b200.engine import CfgPair
+    from lanpaint_b200.runner import VESampling
+    lib = _native.load()
+    dev = cuda_device
+    shape = (20, 4, 128, 128)     # 1.3 M elements
+    x, y, noise, m = synth_inputs(shape, seed=35, device=dev)
+    sig = torch.full((shape[0],), 2.1)
+    times = tuple(O.times_from_sigma(sig, False))
+
+    class Guider:
+        def __init__(self, fused):
+            self.inner_model = self
+            self.model_sampling = VESampling()
+            self.fused = fused
+
+        def __call__(self, xx, t, model_options=None, seed=None):
+            c, u = 0.7 * xx + 0.1 * torch.tanh(xx) + 0.3, 0.7 * xx + 0.1 * torch.tanh(xx) - 0.2
+            pair = CfgPair(c, u, 4.5, -0.5)
+            return pair if self.fused else pair.heads()
+    res = {}
+    try:
+        for key, tma, fused in (("tma", 1, True), ("ldg", 0, True), ("eager", 1, False)):
+            assert lib.lp_set_option(b"tma", tma) == 0
+            torch.manual_seed(29)
+            eng = _engine(Guider(fused), dict(n_steps=3), rng=rng, batched_replace="per_sample")
+            xx = x.clone()
+            out = eng(xx, y, noise, sig, m, times, None, 0, n_steps=3)
+            res[key] = (out, xx)
+        for k in ("ldg", "eager"):
+            assert torch.equal(res["tma"][0], res[k][0]) and torch.equal(res["tma"][1], res[k][1]), k
+    finally:
+        lib.lp_set_option(b"tma", 1)
+
+
+@pytest.mark.parametrize("combine,with_next,with_out", [(False, True, False), (False, True, True), (True, True, True),
+                                                         (False, False, True), (True, False, False)])
+def test_boundary_tma_variant_is_bit_identical(combine, with_next, with_out, cuda_device):
+    """lp_boundary: the cp.async.bulk variant of the step boundary (epilogue + Euler update + next replace step,
+    optional CFG combine) against the LDG kernel and against plain torch, through the C ABI."""
+    from lanpaint_b200 import _native
+    from lanpaint_b200.schedule import Hyper, build_table
+    lib = _native.load()
+    dev = cuda_device
+    B, Cc, S = 6, 4, 128 * 128 + 32 * 16     # ragged last tile
+    shape = (B, Cc, S)
+    gen = torch.Generator(device=dev).manual_seed(1)
+    a, b, y, nz, x0 = (torch.randn(shape, device=dev, generator=gen) for _ in range(5))
+    m8 = (torch.rand(B, 1, S, device=dev, generator=gen) < 0.5).to(torch.uint8)
+    sig = torch.linspace(0.5, 3.0, B)
+    ve, abt, _ = O.times_from_sigma(sig, False)
+    tab = torch.from_numpy(build_table(abt.numpy(), ve.numpy(), Hyper(0.2, 5.0, 1.0, 1.0, False),
+                                       rep_noise=sig.numpy(), rep_y=np.ones(B))).to(dev)
+    dims = _native.Dims(B, Cc * S, S, S, 0, 0)
+    P = C.c_void_p
+    coef, cfg = -0.37, 3.5
+
+    def run(tma):
+        assert lib.lp_set_option(b"tma", tma) == 0
+        x, out = x0.clone(), torch.full(shape, float("nan"), device=dev)
+        h = _native.Heads(a.data_ptr(), b.data_ptr() if combine else None, _native.DTYPE_F32, 1 if combine else 0, cfg, cfg)
+        rc = lib.lp_boundary(C.byref(h), P(y.data_ptr()), P(nz.data_ptr()) if with_next else None, P(m8.data_ptr()),
+                             P(x.data_ptr()), P(out.data_ptr()) if with_out else None, C.c_float(coef),
+                             P(tab.data_ptr()) if with_next else None, C.byref(dims),
+                             P(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        return x, out
+    try:
+        x1, o1 = run(1)
+        x0_, o0 = run(0)
+    finally:
+        lib.lp_set_option(b"tma", 1)
+    assert torch.equal(x1, x0_)
+    known = m8.bool().expand(shape)
+    d = b + (a - b) * cfg if combine else a
+    o = torch.where(known, y, d)
+    xe = torch.addcmul(x0, x0 - o, torch.tensor(coef, device=dev))
+    if with_next:
+        rn = tab[:, _native.T_INVS + 3].view(B, 1, 1)     # LP_T_REPN = 5
+        ry = tab[:, _native.T_INVS + 4].view(B, 1, 1)
+        xe = torch.where(known, rn * nz + ry * y, xe)
+    assert (x1 - xe).abs().max().item() <= 1e-5 * max(1.0, xe.abs().max().item())
+    if with_out:
+        assert torch.equal(o1, o0) and torch.equal(o1, o)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("rng_mode", ["tape", "philox", "torch"])
+def test_half_precision_heads_are_read_in_kernel(dtype, rng_mode, cuda_device):
+    """A model that returns bf16 / fp16 predictions: the kernels read them as they are and widen in registers
+    (lp_heads.dtype) -- no .float() pass.  Reference semantics: type promotion to fp32 when x_t (fp32) meets the
+    half-precision head (lanpaint.py:182-184), i.e. the oracle fed the same rounded heads."""
+    from lanpaint_b200.engine import NoiseTape
+    from lanpaint_b200.runner import SynthDenoiser, VESampling
+    dev = cuda_device
+    shape = (20, 4, 128, 128) if rng_mode != "tape" else (2, 4, 64, 64)
+    x, y, noise, m = synth_inputs(shape, seed=41, device=dev)
+    sig = torch.full((shape[0],), 1.9)
+    times = tuple(O.times_from_sigma(sig, False))
+    n = 3
+
+    class Rounded:     # what the engine sees from a half-precision network, as an fp32-returning model
+        def __init__(self, inner):
+            self.inner, self.inner_model, self.model_sampling = inner, self, inner.model_sampling
+
+        def __call__(self, xx, t, model_options=None, seed=None):
+            return tuple(h.float() for h in self.inner(xx, t))
+    if rng_mode == "tape":
+        hp = O.Hyper(n_steps=n, min_step_frac=1.0)
+        tape = O.NoiseTape(generator=torch.Generator().manual_seed(2))
+
+        class HalfOracle(O.PointwiseDenoiser):
+            def __call__(self, xx, t, model_options=None, seed=None):
+                return tuple(h.to(dtype) for h in super().__call__(xx, t))
+        want_out, want_x = O.outer_step(HalfOracle(O.VESampling()), x.cpu().clone(), y.cpu(), noise.cpu(), sig,
+                                        m.cpu().expand(shape), O.times_from_sigma(sig, False), hp, n_steps=n, draw=tape)
+        eng = _engine(HalfOracle(O.VESampling()), dict(n_steps=n), rng=NoiseTape([d.to(dev) for d in tape.recorded]))
+        xx = x.clone()
+        out = eng(xx, y, noise, sig, m, times, None, 0, n_steps=n)
+        assert max_rel(out, want_out) <= 2e-5 and max_rel(xx, want_x) <= 2e-5
+        return
+    res = {}
+    for key in ("native", "widened"):
+        torch.manual_seed(31)
+        net = SynthDenoiser(VESampling(), dtype=dtype)
+        eng = _engine(net if key == "native" else Rounded(net), dict(n_steps=n), rng=rng_mode, batched_replace="per_sample")
+        xx = x.clone()
+        res[key] = (eng(xx, y, noise, sig, m, times, None, 0, n_steps=n), xx)
+    assert torch.equal(res["native"][0], res["widened"][0]) and torch.equal(res["native"][1], res["widened"][1])
+
+
+def test_two_devices_in_one_process(cuda_device):
+    """Per-device launch state (SM count, dynamic shared memory opt-in, torch's randn geometry) must follow the
+    device of the tensors, not the first device the process touched (ComfyUI multi-GPU, thread-per-device replicas)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from lanpaint_b200.runner import SynthDenoiser, VESampling
+    shape = (20, 4, 128, 128)     # large enough for the TMA-staged kernels (>48 KB dynamic shared memory)
+    outs = {}
+    for rng in ("philox", "torch"):
+        for d in (0, 1):
+            dev = torch.device("cuda", d)
+            x, y, noise, m = synth_inputs(shape, seed=43, device=dev)
+            sig = torch.full((shape[0],), 1.1)
+            times = tuple(O.times_from_sigma(sig, False))
+            torch.cuda.default_generators[d].manual_seed(5)
+            eng = _engine(SynthDenoiser(VESampling()), dict(n_steps=3), rng=rng, batched_replace="per_sample")
+            xx = x.clone()
+            outs[(rng, d)] = (eng(xx, y, noise, sig, m, times, None, 0, n_steps=3).cpu(), xx.cpu())   # current device stays 0
+        assert torch.equal(outs[(rng, 0)][0], outs[(rng, 1)][0]) and torch.equal(outs[(rng, 0)][1], outs[(rng, 1)][1])
+
+
 # ----------------------------------------------------------------------------
 # 9. size-independent property at BASELINE size: the fused update is affine in its operands
 # ----------------------------------------------------------------------------
