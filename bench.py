@@ -1,28 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- Langevin sub-steps/sec on the SDXL 128x128x4 latent (BASELINE.json's metric).
 
-    python bench.py --gpus N --steps K --warmup W              # this repo (CUDA kernels)
-    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path (oracle port)
+    python bench.py --gpus N --steps K --warmup W              # this repo (CUDA kernels), through the node API
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path on the host cores
 
-Workload (`config.workload`): `requests_per_gpu` independent SDXL inpaint requests of
-shape [1,4,128,128] (BASELINE configs[1]'s latent), batched per GPU, each running the
-reference schedule: karras-20 sigmas x N=5 think steps with the node defaults
-(MinStepFrac=1, EarlyStop=1) = 53 Langevin sub-steps + 20 final denoises = 73 model
-calls per request, with the SURVEY-8d synthetic pointwise two-head denoiser
-standing in for the UNet and k-diffusion's Euler update between outer steps.
-One bench "step" = one such job over the GPU's whole batch.  value = request-sub-steps/s
-summed over GPUs (weak scaling: per-GPU batch fixed).
+What is measured (`config.workload`): `requests_per_gpu` independent SDXL inpaint requests of shape [1,4,128,128]
+(BASELINE configs[1]'s latent) batched per GPU, each running the reference schedule: karras-20 sigmas x N=5 think
+steps with the node defaults (MinStepFrac=1, EarlyStop=1) = 53 Langevin sub-steps + 20 final denoises = 73 guider
+evaluations (146 network calls: cond + uncond) per request, a pointwise synthetic network standing in
+for the UNet, sampler "euler".
 
-Timed with CUDA events on the launching stream, barrier + synchronize on both sides, max
-over ranks.  Inputs of the default batch (128 requests: 176 MB touched per launch) exceed
-the 126 MB L2, so every launch streams from HBM (`config.l2`).
+Every job goes through the reference-facing plugin call: `comfy_nodes.LanPaint_KSampler.sample(model, seed, steps,
+cfg, "euler", "karras", positive, negative, LATENT, ...)` -- ComfyUI replaced by `minicomfy` -- with a LATENT dict of
+pinned HOST tensors in and a LATENT dict of host tensors out.  One bench "step" = `jobs_per_step` such calls.
+  value   request-sub-steps/s over the DEVICE time of the sampler loop inside those calls (two CUDA events recorded
+          by the node layer once the inputs are on the device / after the last kernel; max over ranks of the sum)
+  e2e     the same calls by the wall clock: ComfyUI's CPU-side prepare_noise, H2D of latent / noise / mask, the
+          sampler loop, D2H of the result
+The line is emitted for the shipped default rng="torch" (the reference's own randn stream: same seed, same latent);
+`variants.philox` holds the same measurement for the cheaper counter-based stream, `serving` the host-owned
+`runner.GraphedJob` numbers (round-1's headline path), `configs` the literal BASELINE configurations.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -34,8 +37,12 @@ import torch  # noqa: E402
 
 SHAPE = (4, 128, 128)          # SDXL latent of a 1024x1024 image
 N_OUTER, N_INNER = 20, 5
-ALGO_BYTES_PER_ELEM = 28.0 + 1.0 / SHAPE[0]   # read x,x0,x0B,y,C + write x,C (fp32) + uint8 spatial mask
 METRIC = "Langevin sub-steps/sec (SDXL 128x128x4 latent, N=5)"
+
+
+def algo_bytes_per_elem(channels: int, head_bytes: int = 4) -> float:
+    """read x, y, C (fp32) + two heads + write x, C (fp32) + uint8 spatial mask."""
+    return 12.0 + 2.0 * head_bytes + 8.0 + 1.0 / channels
 
 
 def peaks():
@@ -46,54 +53,64 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+# ------------------------------------------------------------------------------------------
+# clocks: NVML sampled in-process from before the warm-up until after the timed region
+# ------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index: int, period: float = 0.02):
+        self.index, self.period = index, period
+        self.rows, self.marks, self.stop_flag, self.thread, self.err = [], {}, False, None, None
 
-    def __enter__(self):
+    def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-            time.sleep(0.15)
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+        except Exception as e:  # no NVML: the line says so instead of inventing numbers
+            self.err = f"{type(e).__name__}: {e}"
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def __exit__(self, *a):
-        if self.proc is not None:
-            time.sleep(0.1)
-            self.proc.terminate()
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.rows.append((time.perf_counter(), sm, rs))
+            except Exception as e:
+                self.err = f"{type(e).__name__}: {e}"
+            time.sleep(self.period)
+
+    def mark(self, name):
+        self.marks[name] = time.perf_counter()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx = max(mx, float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
+        t0, t1 = self.marks.get("t0", 0.0), self.marks.get("t1", float("inf"))
+        inside = [(sm, rs) for (t, sm, rs) in self.rows if t0 <= t <= t1]
+        sm = sorted(v for v, _ in inside)
+        reasons = set()
+        for _, rs in inside:
+            for bit, name in self.REASONS.items():
+                if rs & bit:
                     reasons.add(name)
-        sm.sort()
-        load = [v for v in sm if v > 0.5 * mx] or sm
-        med = load[len(load) // 2] if load else None
-        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": getattr(self, "max_sm", None), "reasons": sorted(reasons),
+                "samples": len(sm), "samples_total": len(self.rows), "source": "NVML in-process, 20 ms period, "
+                "samples inside the timed region", "error": self.err}
 
 
 def bind_to_gpu_numa_node(index: int):
@@ -119,16 +136,19 @@ def bind_to_gpu_numa_node(index: int):
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
 # ------------------------------------------------------------------------------------------
-# the reference arm: the oracle (op-for-op restatement of the reference's eager PyTorch path)
-# on the host cores.  The one place outside tests/ where oracle/ is executed.
+# the reference arm: the reference's own engine (oracle/_ref, bytecode compiled from /root/reference) when it was
+# built, else the oracle port (op-for-op restatement), on the host cores.  The one place outside tests/ where
+# oracle/ is executed.
 # ------------------------------------------------------------------------------------------
+def reference_engine_kind():
+    from oracle import build_ref
+    return "reference" if build_ref.load() is not None else "port"
+
+
 def calibrate_threads(requests: int) -> int:
     """The reference's eager path is ~90 small element-wise ops per sub-step; on a many-core host more
     threads can be much slower (fork/join per op).  Time ONE outer step of the actual workload (5 sub-steps,
@@ -147,8 +167,11 @@ def calibrate_threads(requests: int) -> int:
 
 
 def cpu_job(requests: int, outer_steps: int, threads: int, seed: int = 0):
-    """Runs the first `outer_steps` outer steps of the workload on `requests` requests on the CPU.
+    """Runs the first `outer_steps` outer steps of the workload on `requests` requests on the CPU: k-diffusion's
+    Euler loop and the per-sigma schedule glue (oracle restatement of nodes.py:229-315) around the engine -- the
+    reference's own `LanPaint.__call__` when oracle/_ref is built, the port's `outer_step` otherwise.
     Returns (seconds, request-sub-steps done)."""
+    from oracle import build_ref
     from oracle import langevin_oracle as O
     torch.set_num_threads(threads)
     g = torch.Generator().manual_seed(seed)
@@ -158,36 +181,37 @@ def cpu_job(requests: int, outer_steps: int, threads: int, seed: int = 0):
     sig = O.karras_sigmas(N_OUTER)
     hp = O.Hyper(n_steps=N_INNER, min_step_frac=1.0)
     model = O.PointwiseDenoiser(O.VESampling())
-    counters = {}
+    Ref = build_ref.load()
+    ref_engine = None
+    if Ref is not None:
+        ref_engine = Ref(model, N_INNER, 15.0, hp.lam, hp.beta, hp.step_size, IS_FLUX=False, IS_FLOW=False, MinStepFrac=1.0)
     t0 = time.perf_counter()
-    _cpu_partial(O, model, y, noise, dm, sig, hp, min(outer_steps, N_OUTER), counters)
-    dt = time.perf_counter() - t0
-    return dt, counters["substeps"] * requests
-
-
-def _cpu_partial(O, model, y, noise, dm, sig, hp, outer_steps, counters):
-    """First `outer_steps` outer steps with the FULL schedule's step bookkeeping (n_eff depends on
-    the position in the full 20-step schedule, nodes.py:286-299)."""
     x = model.model_sampling.noise_scaling(sig[0], noise, y)
     mask = O.binarise_mask(dm)
     s_in = x.new_ones([x.shape[0]])
     sub = 0
-    for i in range(outer_steps):
+    for i in range(min(outer_steps, N_OUTER)):
         sigma = sig[i] * s_in
         tm = O.times_from_sigma(sigma, False)
-        n_eff = O.inner_steps_for(sigma, sig, tm.abt, hp.n_steps, 1, 1.0)
-        den, x = O.outer_step(model, x, y, noise, sigma, mask, tm, hp, n_eff)
+        n_eff = O.inner_steps_for(sigma, sig, tm.abt, hp.n_steps, 1, 1.0)   # position in the FULL schedule
+        if ref_engine is not None:
+            den = ref_engine(x, y, noise, sigma, mask, tuple(tm), {}, 0, n_steps=n_eff)   # rewrites x in place
+        else:
+            den, x = O.outer_step(model, x, y, noise, sigma, mask, tm, hp, n_eff)
         x = x + (x - den) / sigma.view(-1, 1, 1, 1) * (sig[i + 1] - sig[i])
         sub += n_eff
-    counters["substeps"] = sub
+    return time.perf_counter() - t0, sub * requests
 
 
 def run_reference(args):
+    import warnings
+    warnings.filterwarnings("ignore")   # the reference's autocast(float32) wrappers warn on CPU (lanpaint.py:201,239)
     rank, world, _ = dist_env()
     if rank != 0:
         return
     host_cores = os.cpu_count() or 1
     req = args.ref_requests
+    kind = reference_engine_kind()
     cores = calibrate_threads(req)
     for _ in range(args.warmup):
         cpu_job(req, N_OUTER, cores)
@@ -197,329 +221,504 @@ def run_reference(args):
         t += dt
         units += u
     value = units / t
-    sample = (f"{req} of {args.requests} requests per step, full karras-20 x N=5 schedule (53 sub-steps/request); "
-              f"{cores} torch threads (fastest of a probe over 1..{host_cores} host cores)")
+    sample = (f"{req} requests per step (the GPU arm batches {args.requests} per call), full karras-20 x N=5 schedule "
+              f"(53 sub-steps/request); {cores} torch threads (fastest of a probe over 1..{host_cores} host cores); engine = "
+              + ("the reference's own LanPaint.__call__ (oracle/_ref bytecode)" if kind == "reference" else "oracle port"))
+    cfg = workload_config(args, "reference")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "sub-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": "sub-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": value, "unit": "sub-steps/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "sub-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args):
-    touched = 5.25 * 4 * args.requests * SHAPE[0] * SHAPE[1] * SHAPE[2] / 1e6
-    return {"workload": "sdxl_1024_inpaint_4x128x128_karras20_N5", "requests_per_gpu": args.requests,
-            "latent_shape": [1] + list(SHAPE), "outer_steps": N_OUTER, "think_steps": N_INNER,
-            "substeps_per_request": 53, "model_calls_per_request": 73, "denoiser": "synthetic pointwise two-head",
-            "sampler": "euler",
-            "mask": "random 50% per spatial site" if args.mask == "random" else "centred 90x90 hole (49.4% unknown)",
-            "rng": args.rng,
-            "launch": {"job-graph": "one CUDA graph per job (20 outer steps), replayed per request batch",
-                       "step-graph": "one CUDA graph per outer step", "eager": "plain launches"}[args.launch],
-            "parallelism": f"replicas x{args.gpus} (requests sharded, no data-path collective)",
-            "l2": (f"inputs larger than L2, no flush: {touched:.0f} MB touched per sub-step launch vs 126 MB L2 (launches "
-                   "stream mostly from HBM; config.sweep shows the L2-resident sizes and the fully HBM-bound R=256; "
-                   "the roofline probe cycles 3 operand sets so it is L2-cold)")
-                  if touched > 126 else f"working set {touched:.0f} MB fits L2; no flush (see config.sweep for HBM-bound size)"}
+def workload_config(args, impl="b200"):
+    n_el = args.requests * SHAPE[0] * SHAPE[1] * SHAPE[2]
+    touched = 5.25 * 4 * n_el / 1e6
+    cfg = {"workload": "sdxl_1024_inpaint_4x128x128_karras20_N5", "requests_per_gpu": args.requests,
+           "latent_shape": [1] + list(SHAPE), "outer_steps": N_OUTER, "think_steps": N_INNER,
+           "substeps_per_request": 53, "model_calls_per_request": 73,
+           "reference_requests": args.ref_requests,
+           "reference_requests_note": "the CPU arm runs a bounded sample of this many requests per step; CPU per-request "
+                                      "throughput rises with batch (BASELINE.md 3), so the CPU figure is a lower bound "
+                                      "of what a larger CPU batch would reach (up to ~2x)",
+           "denoiser": "synthetic pointwise network (one kernel per cond / uncond evaluation)", "sampler": "euler",
+           "mask": "random 50% per spatial site" if args.mask == "random" else "centred 90x90 hole (49.4% unknown)",
+           "parallelism": f"replicas x{args.gpus} (requests sharded, no data-path collective)",
+           "l2": (f"inputs larger than L2, no flush: {touched:.0f} MB touched per sub-step launch vs 126 MB L2 (the "
+                  "roofline probes additionally cycle 3 operand sets so every timed launch is L2-cold)")
+                 if touched > 126 else f"working set {touched:.0f} MB fits L2; no flush"}
+    if impl == "b200":
+        cfg.update({"rng": args.rng, "jobs_per_step": args.jobs_per_step,
+                    "api": "lanpaint_b200.comfy_nodes.LanPaint_KSampler.sample (ComfyUI replaced by minicomfy)"})
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------
-# this repo's arm
+# node-API workloads
 # ------------------------------------------------------------------------------------------
 MASK_KIND = "random"
 
 
-def make_inputs(requests, dev, seed, pinned=False):
-    g = torch.Generator().manual_seed(seed)
-    shape = (requests,) + SHAPE
-    y = torch.randn(shape, generator=g)
-    noise = torch.randn(shape, generator=g)
-    if MASK_KIND == "blob":   # a real inpainting mask: known everywhere except one centred 90x90 hole (49.4 %)
-        mask = torch.ones((requests, 1) + SHAPE[1:])
-        mask[:, :, 19:109, 19:109] = 0.0
-    else:                     # rand(B,1,H,W) < 0.5 per spatial site (worst case for operand skipping)
-        mask = (torch.rand((requests, 1) + SHAPE[1:], generator=g) < 0.5).float()  # 1 = known
-    if pinned:
-        return [t.pin_memory() for t in (y, noise, mask)]
-    return [t.to(dev) for t in (y, noise, mask)]
+class Spec:
+    """One benchmark configuration driven through LanPaint_KSampler.sample."""
+
+    def __init__(self, name, batch, latent, n_inner=5, flow=False, shift=1.0, scheduler="karras", steps=N_OUTER,
+                 cfg=5.0, note=""):
+        self.name, self.batch, self.latent, self.n_inner = name, batch, tuple(latent), n_inner
+        self.flow, self.shift, self.scheduler, self.steps, self.cfg, self.note = flow, shift, scheduler, steps, cfg, note
+
+    @property
+    def shape(self):
+        return (self.batch,) + self.latent
+
+    @property
+    def n_el(self):
+        n = self.batch
+        for d in self.latent:
+            n *= d
+        return n
+
+
+class NodeWorkload:
+    def __init__(self, spec: Spec, dev, rng: str, seed: int = 0, extra_opts=None):
+        import minicomfy
+        minicomfy.install()
+        from lanpaint_b200 import comfy_nodes as N
+        from lanpaint_b200.runner import HostSchedule, SynthCondNet
+        self.N, self.spec, self.dev, self.minicomfy = N, spec, dev, minicomfy
+        g = torch.Generator().manual_seed(seed)
+        shape = spec.shape
+        y = torch.randn(shape, generator=g)
+        mshape = (shape[0], 1) + tuple(shape[2:])
+        if MASK_KIND == "blob" and len(shape) == 4:   # a real inpainting mask: one centred hole of ~half the area
+            nm = torch.zeros(mshape)
+            h, w = shape[2], shape[3]
+            nm[:, :, int(0.15 * h):int(0.85 * h), int(0.15 * w):int(0.85 * w)] = 1.0
+        else:                                           # SURVEY 8d: rand(B,1,*spatial) per site; 1 = regenerate
+            nm = (torch.rand(mshape, generator=g) < 0.5).float()
+        self.latent = {"samples": y.pin_memory(), "noise_mask": nm.pin_memory()}
+        mtype = minicomfy.ModelType.FLOW if spec.flow else minicomfy.ModelType.EPS
+        self.net = SynthCondNet()
+        self.patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(self.net, model_type=mtype, latent_channels=shape[1],
+                                                                 shift=spec.shift), dev)
+        opts = {"rng": rng, "timing": True}
+        opts.update(extra_opts or {})
+        self.patcher.model_options["lanpaint_b200"] = opts
+        self.node = N.LanPaint_KSampler()
+        sig = minicomfy.KSampler(self.patcher, spec.steps, dev, "euler", spec.scheduler).sigmas
+        self.sched = HostSchedule([float(v) for v in sig], 1, spec.n_inner, spec.flow)
+        self.substeps = self.sched.substeps
+        self.guider_calls = self.sched.model_calls
+        self.seed = 1000 * (seed + 1)
+        self.h2d = (y.numel() * 2 + nm.numel()) * 4     # latent + ComfyUI's CPU noise image + the mask as it travels
+        self.d2h = y.numel() * 4
+        self.last_out = None
+
+    def call(self):
+        """One node call; returns (wall seconds, device ms of the sampler loop inside it)."""
+        self.seed += 1
+        t0 = time.perf_counter()
+        (out,) = self.node.sample(self.patcher, self.seed, self.spec.steps, self.spec.cfg, "euler", self.spec.scheduler,
+                                  0.3, -0.2, self.latent, 1.0, self.spec.n_inner, "Image First", "", self.N.IMAGE_MODE)
+        wall = time.perf_counter() - t0            # the result is a host tensor: the call has synchronised
+        e0, e1 = self.N.LAST_RUN["events"]
+        self.last_out = out["samples"]
+        return wall, e0.elapsed_time(e1)
+
+    def warm(self, n=3):
+        for _ in range(n):     # eager -> capture -> replay
+            self.call()
+        return self.N.LAST_RUN["mode"]
+
+    def prepare_noise_ms(self, reps=3):
+        best = float("inf")
+        for k in range(reps):
+            t0 = time.perf_counter()
+            self.minicomfy.prepare_noise(self.latent["samples"], 7 + k)
+            best = min(best, time.perf_counter() - t0)
+        return 1e3 * best
+
+    def stats(self):
+        eng = self.N.LAST_ENGINE["engine"]
+        job = self.N.LAST_RUN["job"]
+        return {"mode": self.N.LAST_RUN["mode"], "fused_sampler": self.N.LAST_RUN["fused"],
+                "graph_nodes_per_job": (eng.launches + 2 * eng.model_calls) if eng is not None else None,
+                "graphs": job.captures if job is not None else None}
+
+
+class DirectGuider:
+    """The object the engine sees from ComfyUI's patched CFGGuider, without ComfyUI: cond / uncond evaluations of
+    the same synthetic network, handed over as a CfgPair (both CFG combines happen in the update kernel)."""
+
+    def __init__(self, net, sampling, cfg, cfg_big):
+        self.inner_model, self.model_sampling, self.net, self.cfg, self.cfg_big = self, sampling, net, cfg, cfg_big
+
+    def __call__(self, x, t, model_options=None, seed=None):
+        from lanpaint_b200.engine import CfgPair
+        return CfgPair(self.net(x, t, 0.3), self.net(x, t, -0.2), self.cfg, self.cfg_big)
 
 
 def run_b200(args):
-    import torch.distributed as dist
+    import minicomfy
+    from lanpaint_b200 import _native
     from lanpaint_b200.engine import LanPaint, pack_mask
-    from lanpaint_b200.runner import GraphedJob, HostSchedule, SynthDenoiser, VESampling, euler_inpaint, karras_sigmas
+    from lanpaint_b200.replicas import ReplicaGroup
+    from lanpaint_b200.runner import (GraphedJob, HostSchedule, SynthCondNet, SynthDenoiser, VESampling, karras_sigmas,
+                                      time_steady_substep)
 
     rank, world, local = dist_env()
     assert torch.cuda.is_available(), "bench.py (impl b200) needs a CUDA device; there is no CPU fallback"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(local) if world > 1 else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    numa = bind_to_gpu_numa_node(local)
+    group = ReplicaGroup(backend="nccl" if world > 1 else None, device=dev)   # init + barrier + max-over-ranks
+    clocks = ClockSampler(local).start()
+    minicomfy.install()
+    R, K, W, J = args.requests, args.steps, max(3, args.warmup), args.jobs_per_step
 
-    R = args.requests
-    model = SynthDenoiser(VESampling())
-    # replicas: the only collective is the one-time broadcast of the denoiser's weights (north_star)
-    w = torch.tensor(model.coef, device=dev)
-    if world > 1:
-        dist.broadcast(w, src=0)
-    model.set_coef(w.tolist())
+    # replicas: the only collective is the one-time broadcast of the network's weights (north_star)
+    weights = torch.tensor(SynthCondNet().coef, device=dev)
+    group.broadcast_weights([weights])
 
-    def make_engine(graph):
-        return LanPaint(model, NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0, StepSize=0.2, MinStepFrac=1.0,
-                        rng=args.rng, batched_replace="per_sample", cuda_graph=graph)
-    eng = make_engine(args.launch == "step-graph")
-    sched = HostSchedule(karras_sigmas(N_OUTER), R, N_INNER)
-    assert sched.substeps == 53 and sched.model_calls == 73
-    y, noise, mask = make_inputs(R, dev, seed=rank)
-    pm = pack_mask(mask, y)
-    torch.manual_seed(1000 + rank)
+    spec_main = Spec("sdxl_batch", R, SHAPE)
+    other_rng = "philox" if args.rng == "torch" else "torch"
 
-    gjob = GraphedJob(eng, sched, (R,) + SHAPE, dev, l2_persist=args.l2_persist) if args.launch == "job-graph" else None
+    def measure(spec, rng, steps, warm_steps, jobs, seed=rank, tag=None):
+        """steps x jobs node calls: device time of the sampler loops (sum, max over ranks) and wall time."""
+        wl = NodeWorkload(spec, dev, rng, seed=seed)
+        wl.net.coef = tuple(weights.tolist())
+        wl.warm(3)
+        for _ in range(warm_steps * jobs):
+            wl.call()
+        group.barrier()
+        if tag == "main":
+            clocks.mark("t0")
+        span_ms, wall_s = 0.0, 0.0
+        for _ in range(steps * jobs):
+            w_, s_ = wl.call()
+            wall_s += w_
+            span_ms += s_
+        group.barrier()
+        if tag == "main":
+            clocks.mark("t1")
+        span_ms, wall_s = group.max_over_ranks(span_ms), group.max_over_ranks(wall_s)
+        units = world * spec.batch * wl.substeps * steps * jobs
+        st = wl.stats()
+        rec = {"value": units / (span_ms * 1e-3), "ms_per_job_device": span_ms / (steps * jobs),
+               "e2e_value": units / wall_s, "ms_per_job_wall": 1e3 * wall_s / (steps * jobs),
+               "jobs": steps * jobs, "substeps_per_request": wl.substeps, "guider_calls_per_request": wl.guider_calls,
+               "launch": st}
+        return rec, wl
 
-    def job():
-        if gjob is not None:
-            return gjob.run(y, noise, pm)
-        return euler_inpaint(eng, y, noise, pm, sched)
+    # ---- main line: the node API at the shipped default -------------------------------------------------------
+    main, wl_main = measure(spec_main, args.rng, K, W, J, tag="main")
+    noise_ms = wl_main.prepare_noise_ms()
+    value, ms_per_step = main["value"], main["ms_per_job_device"] * J
+    e2e = {"value": main["e2e_value"], "unit": "sub-steps/s", "h2d_bytes_per_step": wl_main.h2d * J,
+           "d2h_bytes_per_step": wl_main.d2h * J, "steps": K, "jobs_per_step": J,
+           "ms_per_job_wall": main["ms_per_job_wall"],
+           "breakdown_ms_per_job": {"comfyui_prepare_noise_cpu_randn": noise_ms,
+                                    "sampler_loop_on_device": main["ms_per_job_device"],
+                                    "h2d_d2h_and_host_python": main["ms_per_job_wall"] - noise_ms - main["ms_per_job_device"]},
+           "pcie_gbs": {"note": "latent + noise + mask up, result down, pageable CPU tensors as ComfyUI hands them over",
+                        "bytes_per_job": wl_main.h2d + wl_main.d2h},
+           "numa_node": numa,
+           "api": f"lanpaint_b200.comfy_nodes.LanPaint_KSampler.sample, rng={args.rng}, LATENT dict of pinned host tensors "
+                  "in, LATENT dict of host tensors out (every call: ComfyUI's CPU prepare_noise, H2D, sampler loop, D2H)"}
+    launches = (wl_main.stats()["graph_nodes_per_job"] or 0) * K * J * world
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    # ---- the other randn stream, same measurement (fewer steps) ------------------------------------------------
+    variants = {}
+    if not args.quick:
+        v, _ = measure(spec_main, other_rng, max(2, K // 4), 1, J)
+        variants[other_rng] = {"value": v["value"], "ms_per_job_device": v["ms_per_job_device"],
+                               "e2e": {"value": v["e2e_value"], "unit": "sub-steps/s", "ms_per_job_wall": v["ms_per_job_wall"],
+                                       "api": f"lanpaint_b200.comfy_nodes.LanPaint_KSampler.sample, rng={other_rng}"},
+                               "jobs": v["jobs"], "launch": v["launch"]}
 
-    for _ in range(max(3, args.warmup)):
-        job()
-    barrier()
-
-    # ---- timed region: K jobs, device time, max over ranks ----
-    eng.launches = 0
-    eng.model_calls = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            job()
-        e1.record()
-        barrier()
-    ms = e0.elapsed_time(e1)
-    tmax = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms = float(tmax.item())
-    launches = eng.launches + eng.model_calls   # every synthetic-denoiser call is one kernel of this repo
-    units = world * R * sched.substeps * args.steps
-    value = units / (ms * 1e-3)
-
-    # ---- roofline of the dominant kernel (steady fused sub-step), live CUDA-event timing ----
-    peak, peak_src = peaks()
-    n_el = R * SHAPE[0] * SHAPE[1] * SHAPE[2]
-    algo = ALGO_BYTES_PER_ELEM * n_el
-    roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
-            "kernel": ("lp::substep_tma_kernel<first=0, merge=1> (steady fused sub-step, TMA-staged persistent)"
-                       if args.rng == "philox" and n_el >= (1 << 20) else
-                       "lp::substep_kernel<VEC=4, %s, first=0, fuse_next=1> (steady fused sub-step)" % args.rng),
-            "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": algo}
-    if args.kernel_timer:
-        from lanpaint_b200.runner import time_steady_substep
-        # (1) 53 back-to-back launches of the steady kernel on job-shaped operands, x20 (the roofline number)
-        burst = sorted(time_steady_substep(eng, y, pm, sigma=2.0, launches=53, repeats=20, rotate=3))
-        avg = sum(burst) / len(burst)
-        roof.update(achieved=algo / (avg * 1e-6) / 1e9, avg_us=avg, median_us=burst[len(burst) // 2],
-                    min_us=burst[0], launches_timed=53 * len(burst),
-                    timing="53 back-to-back launches of the steady fused sub-step between two CUDA events on the "
-                           "launching stream, x20, cycling 3 independent job-shaped operand sets so every launch's "
-                           "operands were evicted from L2 by the two launches before it (true HBM streaming)")
-        roof["frac"] = roof["achieved"] / peak
-        warm = sorted(time_steady_substep(eng, y, pm, sigma=2.0, launches=53, repeats=10, rotate=1))
-        roof["same_buffers_us"] = sum(warm) / len(warm)   # one operand set re-used: the L2 keeps part of it
-        # (2) the same kernel inside real jobs: one CUDA-event pair around every launch of an eager pass
-        # (includes the ~launch latency an isolated launch pays; reported for the share-of-step cross-check)
-        eng_t = make_engine(False)
-        for _ in range(2):
-            euler_inpaint(eng_t, y, noise, pm, sched)
-        barrier()
-        eng_t.kernel_timer = timer = []
-        for _ in range(max(3, min(10, args.steps))):
-            euler_inpaint(eng_t, y, noise, pm, sched)
-        barrier()
-        eng_t.kernel_timer = None
-        mid = sorted(a.elapsed_time(b) * 1e3 for f, a, b in timer if (f & 3) == 2)  # steady = FUSE_NEXT, not FIRST
-        if mid:
-            roof["in_job_event_pair_us"] = sum(mid) / len(mid)
-        roof["substep_share_of_step"] = 53 * avg * 1e-3 / (ms / args.steps)
-        tr = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr):
-            roof["traffic"] = json.load(open(tr)).get(str(R))
-
-    if args.kernel_timer and rank == 0:
-        # context for the fraction above: the same copy probe MEASURED_PEAKS.json was produced with
-        # (torch b.copy_(a) over 1 Gi bf16 elements, read+write bytes, best of 10), on THIS box
-        try:
-            a_ = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
-            b_ = torch.empty_like(a_)
-            best = float("inf")
-            for _ in range(10):
-                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                c0.record()
-                b_.copy_(a_)
-                c1.record()
-                c1.synchronize()
-                best = min(best, c0.elapsed_time(c1))
-            roof["copy_gbs_this_box"] = 2 * a_.numel() * 2 / (best * 1e-3) / 1e9
-            del a_, b_
-        except Exception:
-            pass
-
-    # ---- e2e: host buffers in, host result out, through the public call; copies inside the timed region.
-    # Two request batches are in flight on two streams (each with its own pinned buffers and job graph), so
-    # the H2D of batch k+1 and the D2H of batch k-1 overlap the kernels of batch k, as a serving loop does.
-    e2e = None
-    if not args.no_e2e:
+    # ---- serving path: runner.GraphedJob (host-owned sampler loop, whole job = one graph), same guider ---------
+    serving = None
+    if not args.quick:
+        serving = {}
+        sched = HostSchedule(karras_sigmas(N_OUTER), R, N_INNER)
+        g = torch.Generator().manual_seed(50 + rank)
+        y = torch.randn((R,) + SHAPE, generator=g).to(dev)
+        noise = torch.randn((R,) + SHAPE, generator=g).to(dev)
+        known = (torch.rand((R, 1) + SHAPE[1:], generator=g) < 0.5).to(dev)
+        pm = pack_mask(known, y)
+        for rng in (args.rng, other_rng):
+            net = SynthCondNet(tuple(weights.tolist()))
+            eng = LanPaint(DirectGuider(net, VESampling(), 5.0, 5.0), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0,
+                           StepSize=0.2, MinStepFrac=1.0, rng=rng, batched_replace="per_sample")
+            job = GraphedJob(eng, sched, (R,) + SHAPE, dev)
+            for _ in range(3):
+                job.run(y, noise, pm)
+            group.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_jobs = max(20, K)
+            e0.record()
+            for _ in range(n_jobs):
+                job.run(y, noise, pm)
+            e1.record()
+            group.barrier()
+            ms = group.max_over_ranks(e0.elapsed_time(e1))
+            serving[rng] = {"value": world * R * sched.substeps * n_jobs / (ms * 1e-3), "ms_per_job": ms / n_jobs,
+                            "graph_nodes_per_job": job.launches + 2 * job.model_calls,
+                            "api": "lanpaint_b200.runner.GraphedJob.run, device-resident inputs, one CUDA graph per job"}
+            del job, eng
+        ref_ms = serving[args.rng]["ms_per_job"]
+        serving["node_api_over_graphed_job"] = main["ms_per_job_device"] / ref_ms
+        # host tensors in, host result out through the same object, two batches in flight, uint8 mask, noise drawn on
+        # the device (serving hosts do not need ComfyUI's CPU noise image): round 1's e2e, with less PCIe traffic
         lanes = []
-        for lane in range(2 if gjob is not None else 1):
-            hy, hn, hm = make_inputs(R, dev, seed=rank + 17 * lane, pinned=True)
-            lanes.append({"in": (hy, hn, hm), "out": torch.empty((R,) + SHAPE).pin_memory(),
-                          "stream": torch.cuda.Stream(device=dev),
-                          "job": GraphedJob(make_engine(False), sched, (R,) + SHAPE, dev,
-                                            l2_persist=args.l2_persist) if gjob is not None else None})
-        bi = sum(t.numel() * 4 for t in lanes[0]["in"])
-        bo = lanes[0]["out"].numel() * 4
+        for lane in range(2):
+            gl = torch.Generator().manual_seed(70 + rank + 17 * lane)
+            hy = torch.randn((R,) + SHAPE, generator=gl).pin_memory()
+            hm = (torch.rand((R, 1) + SHAPE[1:], generator=gl) < 0.5).to(torch.uint8).pin_memory()
+            net = SynthCondNet(tuple(weights.tolist()))
+            eng = LanPaint(DirectGuider(net, VESampling(), 5.0, 5.0), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0,
+                           StepSize=0.2, MinStepFrac=1.0, rng=args.rng, batched_replace="per_sample")
+            lanes.append({"y": hy, "m": hm, "out": torch.empty((R,) + SHAPE).pin_memory(),
+                          "stream": torch.cuda.Stream(device=dev), "job": GraphedJob(eng, sched, (R,) + SHAPE, dev)})
 
-        def e2e_submit(ln):
-            hy, hn, hm = ln["in"]
+        def submit(ln):
             with torch.cuda.stream(ln["stream"]):
-                if ln["job"] is not None:   # pinned host tensors straight into the job's static buffers
-                    ln["job"].run(hy, hn, hm.to(dev, non_blocking=True), x_out=ln["out"])
-                else:
-                    dy, dn, dm = (t.to(dev, non_blocking=True) for t in (hy, hn, hm))
-                    euler_inpaint(eng, dy, dn, dm, sched, x_out=ln["out"])
+                ln["job"].run(ln["y"], None, ln["m"].to(dev, non_blocking=True), x_out=ln["out"])
 
-        def e2e_run(n):
+        def run_lanes(n):
             for i in range(n):
-                ln = lanes[i % len(lanes)]
+                ln = lanes[i % 2]
                 ln["stream"].synchronize()      # the previous result of this lane is on the host: the user has it
-                e2e_submit(ln)
+                submit(ln)
             for ln in lanes:
                 ln["stream"].synchronize()
-
-        e2e_run(2 * len(lanes))
-        barrier()
-        k2 = max(4, args.steps // 2)
+        run_lanes(6)
+        group.barrier()
+        n_jobs = max(20, K)
         t0 = time.perf_counter()
-        e2e_run(k2)
-        barrier()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * R * sched.substeps * k2 / float(tt.item()), "unit": "sub-steps/s",
-               "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "steps": k2, "in_flight": len(lanes),
-               "numa_node_rank0": numa,
-               "api": ("lanpaint_b200.runner.GraphedJob.run" if gjob is not None else "lanpaint_b200.runner.euler_inpaint")
-                      + "(engine=lanpaint_b200.LanPaint) on pinned host tensors, result to pinned host memory"}
+        run_lanes(n_jobs)
+        group.barrier()
+        dt = group.max_over_ranks(time.perf_counter() - t0)
+        bi = lanes[0]["y"].numel() * 4 + lanes[0]["m"].numel()
+        bo = lanes[0]["out"].numel() * 4
+        serving["e2e"] = {"value": world * R * sched.substeps * n_jobs / dt, "unit": "sub-steps/s",
+                          "h2d_bytes_per_job": bi, "d2h_bytes_per_job": bo, "jobs": n_jobs, "in_flight": 2,
+                          "pcie_gbs": {"h2d": bi * n_jobs / dt / 1e9, "d2h": bo * n_jobs / dt / 1e9},
+                          "api": f"lanpaint_b200.runner.GraphedJob.run(latent pinned host, noise=None (drawn on the device), "
+                                 f"uint8 mask pinned host) -> pinned host result, rng={args.rng}"}
+        del lanes
 
-    # ---- CPU baseline: the oracle port on the host cores, bounded sample (rank 0, N=1 only) ----
+    # ---- rooflines: the steady fused sub-step of each stream (and with bf16 heads), live CUDA-event timing ------
+    peak, peak_src = peaks()
+    roofs = {}
+    if args.kernel_timer:
+        g = torch.Generator().manual_seed(90 + rank)
+        y = torch.randn((R,) + SHAPE, generator=g).to(dev)
+        known = (torch.rand((R, 1) + SHAPE[1:], generator=g) < 0.5).to(dev)
+        pm = pack_mask(known, y)
+        n_el = R * SHAPE[0] * SHAPE[1] * SHAPE[2]
+        kernels = {"torch": ("lp::substep_torch_tma_kernel<float, first=0, next=1> (steady fused sub-step, torch.randn stream, "
+                             "producer warp + 4 plane slots of cp.async.bulk)", torch.float32),
+                   "philox": ("lp::substep_tma_kernel<float, first=0, next=1, merge=1> (steady fused sub-step, philox stream, "
+                              "TMA-staged persistent)", torch.float32),
+                   "torch_bf16_heads": ("lp::substep_torch_tma_kernel<bf16, first=0, next=1>", torch.bfloat16),
+                   "philox_bf16_heads": ("lp::substep_tma_kernel<bf16, first=0, next=1, merge=1>", torch.bfloat16)}
+        for key, (kname, hdtype) in kernels.items():
+            rng = key.split("_")[0]
+            eng = LanPaint(SynthDenoiser(VESampling(), dtype=hdtype), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0,
+                           StepSize=0.2, MinStepFrac=1.0, rng=rng, batched_replace="per_sample")
+            algo = algo_bytes_per_elem(SHAPE[0], 4 if hdtype == torch.float32 else 2) * n_el
+            burst = sorted(time_steady_substep(eng, y, pm, sigma=2.0, launches=53, repeats=20, rotate=3))
+            avg = sum(burst) / len(burst)
+            rec = {"bound": "hbm", "achieved": algo / (avg * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                   "frac": algo / (avg * 1e-6) / 1e9 / peak, "traffic": None, "kernel": kname, "peak_source": peak_src,
+                   "algorithmic_bytes_per_launch": algo, "avg_us": avg, "median_us": burst[len(burst) // 2],
+                   "min_us": burst[0], "launches_timed": 53 * len(burst)}
+            if key in ("torch", "philox"):
+                warm = sorted(time_steady_substep(eng, y, pm, sigma=2.0, launches=53, repeats=10, rotate=1))
+                rec["same_buffers_us"] = sum(warm) / len(warm)   # one operand set re-used: the L2 keeps part of it
+            tr = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tr):
+                rec["traffic"] = json.load(open(tr)).get(f"{key}_{R}", json.load(open(tr)).get(str(R)) if key == "philox" else None)
+            roofs[key] = rec
+        roofs[args.rng]["timing"] = ("53 back-to-back launches of the steady fused sub-step between two CUDA events on the "
+                                     "launching stream, x20, cycling 3 independent job-shaped operand sets so every launch's "
+                                     "operands were evicted from L2 by the two launches before it (true HBM streaming)")
+        roofs[args.rng]["substep_share_of_step"] = 53 * roofs[args.rng]["avg_us"] * 1e-3 / main["ms_per_job_device"]
+        if rank == 0:
+            # context for the fractions: the same copy probe MEASURED_PEAKS.json was produced with, on THIS box
+            try:
+                a_ = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+                b_ = torch.empty_like(a_)
+                best = float("inf")
+                for _ in range(10):
+                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    c0.record()
+                    b_.copy_(a_)
+                    c1.record()
+                    c1.synchronize()
+                    best = min(best, c0.elapsed_time(c1))
+                roofs[args.rng]["copy_gbs_this_box"] = 2 * a_.numel() * 2 / (best * 1e-3) / 1e9
+                del a_, b_
+            except Exception:
+                pass
+        torch.cuda.empty_cache()
+    roof = roofs.get(args.rng) or {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                                   "traffic": None, "peak_source": peak_src}
+
+    # ---- the literal BASELINE configurations, each through the node API ------------------------------------------
+    configs = None
+    specs = [Spec("cfg2_sdxl_batch1_N5", 1, SHAPE, note="BASELINE configs[1]"),
+             Spec("sdxl_batch8_N5", 8, SHAPE, note="north_star target shape"),
+             Spec("cfg3_sdxl_4_per_gpu_N10", 4, SHAPE, n_inner=10, note="BASELINE configs[2]: batch 32 = 4 per GPU x 8"),
+             Spec("cfg4_flux_16x128x128_flow_simple20", 1, (16, 128, 128), flow=True, shift=1.0, scheduler="simple",
+                  cfg=1.0 + 2.5, note="BASELINE configs[3] at the ComfyUI boundary (patchify is inside the DiT)"),
+             Spec("cfg5_wan_16x21x80x45_flow_simple20_shift3", 1, (16, 21, 80, 45), flow=True, shift=3.0, scheduler="simple",
+                  note="BASELINE configs[4], 81 frames -> 21 latent frames, one GPU holds the sample (see --frame-shard)")]
+    if args.configs and not args.quick:
+        configs = []
+        for sp in specs:
+            if world > 1 and not sp.name.startswith("cfg3"):
+                continue           # SCALE carries cfg3 (32 requests over 8 GPUs); the rest are single-GPU records
+            recs = {}
+            for rng in (args.rng, other_rng):
+                r_, wl = measure(sp, rng, 1, 0, 12 if sp.batch <= 8 else 6, seed=rank + 3)
+                recs[rng] = r_
+            r0 = recs[args.rng]
+            c = {"name": sp.name, "note": sp.note, "latent_shape": list(sp.shape), "think_steps": sp.n_inner,
+                 "schedule": f"{sp.scheduler}-{sp.steps}" + (f" shift {sp.shift}" if sp.flow else ""),
+                 "substeps": r0["substeps_per_request"], "guider_calls": r0["guider_calls_per_request"],
+                 "n_gpus": world, "api": "comfy_nodes.LanPaint_KSampler.sample"}
+            for rng, r_ in recs.items():
+                nodes = r_["launch"]["graph_nodes_per_job"]
+                algo = algo_bytes_per_elem(sp.latent[0]) * sp.n_el * r_["substeps_per_request"]
+                c[rng] = {"value": r_["value"], "ms_per_job_device": r_["ms_per_job_device"], "e2e_value": r_["e2e_value"],
+                          "ms_per_job_wall": r_["ms_per_job_wall"], "launch_mode": r_["launch"]["mode"],
+                          "graph_nodes_per_job": nodes,
+                          "us_per_graph_node": 1e3 * r_["ms_per_job_device"] / nodes if nodes else None,
+                          "substep_algorithmic_gbs": algo / (r_["ms_per_job_device"] * 1e-3) / 1e9,
+                          "regime": "latency / L2 (working set %.1f MB per launch)" % (5.25 * 4 * sp.n_el / 1e6)}
+            if rank == 0 and world == 1:
+                c["reference_eager_on_this_gpu"] = eager_reference_on_gpu(sp, dev)
+                if c["reference_eager_on_this_gpu"].get("ms_per_job"):
+                    c["speedup_vs_reference_on_this_gpu"] = (c["reference_eager_on_this_gpu"]["ms_per_job"] /
+                                                            c[args.rng]["ms_per_job_device"])
+            configs.append(c)
+            torch.cuda.empty_cache()
+
+    # ---- cfg5 frame-sharded synthetic run: one sample's frames split over the ranks ------------------------------
+    frame_shard = None
+    if args.frame_shard and not args.quick:
+        frame_shard = run_frame_shard(group, dev, args)
+
+    # ---- CPU baseline: the reference on the host cores, bounded sample (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        import warnings
+        warnings.filterwarnings("ignore")
         host_cores = os.cpu_count() or 1
+        kind = reference_engine_kind()
         cores = calibrate_threads(args.ref_requests)
         cpu_job(2, 2, cores)  # warm
         dt, u = cpu_job(args.ref_requests, N_OUTER, cores)
-        # the same port with device="cuda": what a user of the reference runs today on this very GPU
-        # (eager PyTorch, ~89 element-wise launches per sub-step).  Informational, not the reference arm.
-        gpu_eager = None
-        try:
-            from oracle import langevin_oracle as O
-            rq = args.ref_requests
-            yq, nq, mq = make_inputs(rq, dev, seed=3)
-            sq = O.karras_sigmas(N_OUTER).to(dev)
-            hq = O.Hyper(n_steps=N_INNER, min_step_frac=1.0)
-            dmq = (1 - mq).expand_as(yq).contiguous()
-            cnt = {}
-            O.euler_inpaint(O.PointwiseDenoiser(O.VESampling()), yq, nq, dmq, sq, hq, counters=cnt)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            O.euler_inpaint(O.PointwiseDenoiser(O.VESampling()), yq, nq, dmq, sq, hq, counters=cnt)
-            torch.cuda.synchronize()
-            tq = time.perf_counter() - t0
-            gpu_eager = {"value": rq * cnt["substeps"] / tq, "unit": "sub-steps/s", "requests": rq,
-                         "ms_per_job": 1e3 * tq, "what": "oracle port, device=cuda, eager launches, same schedule"}
-        except Exception as e:  # never let the informational leg break the bench line
-            gpu_eager = {"error": f"{type(e).__name__}: {e}"}
-        cpu = {"value": u / dt, "unit": "sub-steps/s", "cores": cores, "kind": "port", "same_port_on_this_gpu": gpu_eager,
+        cpu = {"value": u / dt, "unit": "sub-steps/s", "cores": cores, "kind": kind,
+               "same_reference_math_on_this_gpu": eager_reference_on_gpu(Spec("sdxl_batch8", args.ref_requests, SHAPE), dev),
                "sample": f"{args.ref_requests} of {R} requests, full karras-20 x N=5 schedule, {dt:.1f} s of CPU work; "
-                         f"{cores} torch threads (fastest of a probe over 1..{host_cores} host cores)"}
+                         f"{cores} torch threads (fastest of a probe over 1..{host_cores} host cores); engine = "
+                         + ("the reference's own LanPaint.__call__ (oracle/_ref bytecode)" if kind == "reference" else "oracle port")}
 
-    # ---- the literal BASELINE configs (batch 1, batch 8) and the L2-resident regime, same method as `value` ----
-    sweep = None
-    if rank == 0 and world == 1 and args.sweep:
-        sweep = []
-        for r in (1, 8, 32, 64, 256):
-            if r == R:
-                continue
-            m_r = SynthDenoiser(VESampling())
-            e_r = LanPaint(m_r, NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0, StepSize=0.2, MinStepFrac=1.0,
-                           rng=args.rng, batched_replace="per_sample")
-            s_r = HostSchedule(karras_sigmas(N_OUTER), r, N_INNER)
-            y_r, n_r, k_r = make_inputs(r, dev, seed=5)
-            j_r = GraphedJob(e_r, s_r, (r,) + SHAPE, dev)
-            p_r = pack_mask(k_r, y_r)
-            for _ in range(3):
-                j_r.run(y_r, n_r, p_r)
-            torch.cuda.synchronize()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            for _ in range(40 if r <= 64 else 12):
-                j_r.run(y_r, n_r, p_r)
-            a1.record()
-            torch.cuda.synchronize()
-            t_r = a0.elapsed_time(a1) / (40 if r <= 64 else 12)
-            sweep.append({"requests_per_gpu": r, "ms_per_step": t_r, "value": r * s_r.substeps / (t_r * 1e-3),
-                          "note": "working set fits L2" if r <= 64 else "every launch streams from HBM"})
-            del j_r, e_r, m_r, y_r, n_r, k_r, p_r
-            torch.cuda.empty_cache()
-
+    clocks.stop()
     if rank == 0:
+        cfg = workload_config(args)
+        cfg["timing"] = ("value: sum over the timed calls of the device time between two CUDA events the node layer records "
+                         "inside KSAMPLER.sample (inputs on the device -> last kernel of the sampler loop), barrier + "
+                         "synchronize on both sides of the timed region, max over ranks; e2e: wall clock of the same calls")
+        cfg["launch"] = main["launch"]
+        if configs is not None:
+            cfg["configs"] = configs
         line = {
-            "metric": METRIC, "value": value, "unit": "sub-steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": value, "unit": "sub-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches * world, "clocks": clocks.summary(),
+            "config": cfg, "roofline": roof, "rooflines": roofs, "cpu_baseline": cpu, "e2e": e2e,
+            "variants": variants, "serving": serving, "frame_shard": frame_shard,
+            "gpu_launches": launches, "clocks": clocks.summary(),
         }
-        if sweep is not None:
-            line["config"]["sweep"] = sweep
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    group.close()
+
+
+def eager_reference_on_gpu(spec: Spec, dev):
+    """The reference's math (oracle port, op for op) with device="cuda": what a user of the reference runs today on
+    this very GPU (eager PyTorch, ~89 element-wise launches per sub-step).  Informational, not the reference arm."""
+    try:
+        from oracle import langevin_oracle as O
+        import minicomfy
+        g = torch.Generator().manual_seed(3)
+        shape = spec.shape
+        y = torch.randn(shape, generator=g).to(dev)
+        noise = torch.randn(shape, generator=g).to(dev)
+        dm = (torch.rand((shape[0], 1) + tuple(shape[2:]), generator=g) < 0.5).float().to(dev).expand(shape).contiguous()
+        if spec.flow:
+            sig = minicomfy.simple_scheduler(minicomfy.ModelSamplingCONST(spec.shift), spec.steps).to(dev)
+            sampling = O.FlowSampling()
+        else:
+            sig = O.karras_sigmas(spec.steps).to(dev)
+            sampling = O.VESampling()
+        hp = O.Hyper(n_steps=spec.n_inner, min_step_frac=1.0, flow=spec.flow)
+        cnt = {}
+        O.euler_inpaint(O.PointwiseDenoiser(sampling), y, noise, dm, sig, hp, counters=cnt)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        O.euler_inpaint(O.PointwiseDenoiser(sampling), y, noise, dm, sig, hp, counters=cnt)
+        torch.cuda.synchronize()
+        tq = time.perf_counter() - t0
+        return {"value": shape[0] * cnt["substeps"] / tq, "unit": "sub-steps/s", "requests": shape[0],
+                "ms_per_job": 1e3 * tq, "what": "oracle port, device=cuda, eager launches, same schedule"}
+    except Exception as e:  # never let the informational leg break the bench line
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
+def run_frame_shard(group, dev, args):
+    """BASELINE configs[4] in its synthetic form: ONE Wan sample [1,16,21,80,45], its 21 latent
+    frames split over the ranks; the update kernels need no exchange, the early stopper's two masked sums are the
+    only cross-shard quantity (one all_reduce of 2 doubles per check)."""
+    from lanpaint_b200.frame_shard import FrameShardedRun
+    try:
+        run = FrameShardedRun(group, dev, latent=(16, 21, 80, 45), n_inner=N_INNER, steps=N_OUTER, shift=3.0,
+                              early_stop_threshold=args.frame_shard_threshold)
+        return run.bench(jobs=10)
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--requests", type=int, default=128, help="independent SDXL requests batched per GPU")
+    ap.add_argument("--jobs-per-step", type=int, default=16,
+                    help="node calls per bench step (16 x ~3.5 ms of device time x 20 steps > 1 s timed)")
     ap.add_argument("--ref-requests", type=int, default=8, help="requests per step in the CPU arm's bounded sample")
-    ap.add_argument("--rng", default="philox", choices=["philox", "torch"])
-    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--rng", default="torch", choices=["philox", "torch"],
+                    help="torch (default, what the nodes ship: the reference's own randn stream) | philox")
+    ap.add_argument("--quick", action="store_true", help="main line + rooflines only")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-sweep", dest="sweep", action="store_false", help="skip the R=1/8/32 lines in config.sweep")
+    ap.add_argument("--no-configs", dest="configs", action="store_false", help="skip the BASELINE configuration records")
     ap.add_argument("--no-kernel-timer", dest="kernel_timer", action="store_false")
-    ap.add_argument("--l2-persist", action="store_true", help="pin the clean latent in L2 (measured slower; off)")
-    ap.add_argument("--launch", default="job-graph", choices=["job-graph", "step-graph", "eager"],
-                    help="one CUDA graph per job (default) | one per outer step | plain launches")
+    ap.add_argument("--no-frame-shard", dest="frame_shard", action="store_false")
+    ap.add_argument("--frame-shard-threshold", type=float, default=0.0,
+                    help="> 0: run the frame-sharded record with the early stopper on (one all_reduce per check)")
     ap.add_argument("--mask", default="random", choices=["random", "blob"],
-                    help="random 50%% per site (SURVEY 8d, default) | one centred hole of the same area")
+                    help="random 50%% per site (SURVEY 8d, default) | one centred hole of about the same area")
     args = ap.parse_args()
     global MASK_KIND
     MASK_KIND = args.mask

@@ -151,6 +151,11 @@ int lp_set_option(const char* name, int value);
  * pseudo-random ones plus every edge case, for which it disagrees with n / d.  0 = sound. */
 int64_t lp_selftest_index_math(int64_t samples);
 
+/* Device self test of the FP32x2 (FFMA2) Box-Muller the torch-stream kernels use: runs it next to the scalar cuRAND
+ * form on `n` pseudo-random input quadruples (plus 4096 edge cases: extremes of u and v, u == 1) and counts bitwise
+ * mismatches into *mismatches_dev (a device uint64, zeroed by the call).  0 = the two are interchangeable. */
+int lp_selftest_box_muller(int64_t n, uint64_t seed, unsigned long long* mismatches_dev, lp_stream_t stream);
+
 /* ---- host: coefficient table ------------------------------------------- */
 /* Replaces LanPaint.prepare_step_size + the mask blend of A/D/dt + the
  * exp/expm1/where/sqrt of advance_time_overdamped (lanpaint.py:81,205-214,

@@ -174,12 +174,19 @@ def reshape_mask(input_mask, output_shape, video_inpainting=False):
 
 
 def prepare_mask(noise_mask, shape, device, video_inpainting=False):
-    """Same values and shape as the reference's prepare_mask (nodes.py:119-130).  When the source mask has a
-    single channel the result is that channel moved to `device` and *expanded* (stride 0) over the latent's
-    channels instead of repeated: 1/C of the bytes cross PCIe, and `_latent_mask` can see without a device
-    read-back that one uint8 per spatial site is enough."""
+    """Same values and shape as the reference's prepare_mask (nodes.py:119-130).  Two savings on the way to the
+    device: a mask with a single channel stays single-channel across PCIe and is *expanded* (stride 0) over the
+    latent's channels instead of repeated (1/C of the bytes; `_latent_mask` then sees without a device read-back
+    that one uint8 per spatial site is enough), and a mask that already has the latent's spatial size (nothing to
+    resample) travels in its own dtype -- uint8 / bool masks as one byte per site -- and is widened on the device."""
     m = noise_mask
     one_channel = m.ndim <= 3 or m.shape[1] == 1
+    no_resample = (not video_inpainting) and m.ndim >= 2 and tuple(m.shape[-(len(shape) - 2):]) == tuple(shape[2:]) \
+        and m.ndim in (len(shape) - 2, len(shape) - 1, len(shape))
+    if no_resample:
+        m = m.to(device)
+        if not m.is_floating_point():
+            m = m.float()
     if one_channel and len(shape) >= 3 and shape[1] > 1:
         compact = reshape_mask(m, (shape[0], 1) + tuple(shape[2:]), video_inpainting).to(device)
         return compact.expand(tuple(shape))

@@ -201,7 +201,8 @@ int launch_boundary_tma(const BoundaryArgs& p, cudaStream_t s) {
   constexpr int kTile = 2048, kStages = 2;
   const int dev = current_device();
   const size_t smem = sizeof(BoundaryStage<H, kTile>) * kStages;
-  ensure_dynamic_smem(boundary_tma_kernel<H, kCombine, kNext, kTile, kStages>, smem, dev);
+  static bool configured[kMaxDevices] = {};  // per instantiation of this launcher
+  ensure_dynamic_smem(boundary_tma_kernel<H, kCombine, kNext, kTile, kStages>, smem, dev, configured);
   BTileGeom tg;
   tg.channels = p.g.per_row.d / p.g.spatial.d;
   tg.tiles_per_channel = (p.g.spatial.d + kTile - 1) / kTile;

@@ -130,6 +130,30 @@ __global__ void __launch_bounds__(kBlock) fill_normal_torch_kernel(float* out, u
   }
 }
 
+// bitwise comparison of the FP32x2 Box-Muller with the scalar cuRAND form over pseudo-random and edge-case inputs
+__global__ void __launch_bounds__(kBlock) selftest_box_muller_kernel(uint64_t n, uint64_t seed, unsigned long long* bad) {
+  const uint64_t gid = (uint64_t)blockIdx.x * kBlock + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * kBlock;
+  unsigned long long mine = 0;
+  for (uint64_t i = gid; i < n; i += stride) {
+    uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), 0x5eedu, 0u),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    if (i < 4096) {  // edge cases: the extremes of u and v in every combination, u == 1 (log = 0), smallest u
+      const uint32_t edge[8] = {0u, 1u, 0x7fffffffu, 0x80000000u, 0xffffff00u, 0xffffff7fu, 0xffffff80u, 0xffffffffu};
+      r.x = edge[i & 7];
+      r.y = edge[(i >> 3) & 7];
+      r.z = edge[(i >> 6) & 7];
+      r.w = edge[(i >> 9) & 7];
+    }
+    const float2 a = box_muller_curand(r.x, r.y), b = box_muller_curand(r.z, r.w);
+    float2 c, d;
+    box_muller_curand_x2(r.x, r.y, r.z, r.w, c, d);
+    mine += (__float_as_uint(a.x) != __float_as_uint(c.x)) + (__float_as_uint(a.y) != __float_as_uint(c.y)) +
+            (__float_as_uint(b.x) != __float_as_uint(d.x)) + (__float_as_uint(b.y) != __float_as_uint(d.y));
+  }
+  if (mine) atomicAdd(bad, mine);
+}
+
 template <int N, typename H>
 __global__ void __launch_bounds__(kBlock) synth_denoiser_kernel(const float* __restrict__ x, H* h0, H* h1, uint32_t n,
                                                                 float a0, float b0, float c0, float a1, float c1) {
@@ -225,6 +249,16 @@ extern "C" int64_t lp_selftest_index_math(int64_t samples) {
     check(n, d);
   }
   return bad;
+}
+
+extern "C" int lp_selftest_box_muller(int64_t n, uint64_t seed, unsigned long long* mismatches_dev, lp_stream_t stream) {
+  if (n < 0 || !mismatches_dev) return LP_ERR_INVALID;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemsetAsync(mismatches_dev, 0, sizeof(unsigned long long), s) != cudaSuccess) return (check_launch(), LP_ERR_CUDA);
+  if (n == 0) return LP_OK;
+  const unsigned grid = (unsigned)device_info(current_device()).sms * 8u;
+  launch_kernel(selftest_box_muller_kernel, dim3(grid), s, (uint64_t)n, seed, mismatches_dev);
+  return check_launch();
 }
 
 extern "C" int lp_torch_randn_geometry(int64_t numel, int device, int64_t* grid_out, uint64_t* increment_out) {

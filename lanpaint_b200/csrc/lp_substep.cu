@@ -261,29 +261,26 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) substep_tma_kernel(const S
 //   * consumer thread c owns subsequences 4c..4c+3 of the block: 4 Philox calls per draw, cuRAND's exact
 //     Box-Muller, and its four normals per plane are one float4 of that plane's sub-tile -- no shuffles.
 // Same Philox stream, same arithmetic as the LDG kernels: bit-identical results.
-constexpr int kTorchG = 1024;
-constexpr int kTorchConsumers = 256;
-constexpr int kTorchThreads = kTorchConsumers + 32;
-
-template <typename H>
+template <typename H, int kG>
 struct __align__(128) TorchSlot {
-  float x[kTorchG];
-  H x0[kTorchG], x0b[kTorchG];
-  float y[kTorchG], c[kTorchG];
-  uint8_t m[kTorchG];
+  float x[kG];
+  H x0[kG], x0b[kG];
+  float y[kG], c[kG];
+  uint8_t m[kG];
 };
 
 struct TorchTmaGeom {
-  uint32_t groups_per_call;  // T / kTorchG
+  uint32_t groups_per_call;  // T / kG
   uint32_t n_groups;         // calls * groups_per_call
 };
 
-template <typename H, bool kFirst, bool kNext>
-__global__ void __launch_bounds__(kTorchThreads, 2) substep_torch_tma_kernel(const SubstepArgs a, const TorchTmaGeom tg) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  using Slot = TorchSlot<H>;
+// kG subsequences per group = 4 per consumer thread; one extra warp produces.
+template <typename H, bool kFirst, bool kNext, int kG>
+__device__ __forceinline__ void torch_tma_body(const SubstepArgs& a, const TorchTmaGeom& tg, unsigned char* smem_raw,
+                                               uint64_t* full, uint64_t* empty) {
+  constexpr int kConsumers = kG / 4;
+  using Slot = TorchSlot<H, kG>;
   Slot* slot = reinterpret_cast<Slot*>(smem_raw);
-  __shared__ __align__(8) uint64_t full[4], empty[4];
   pdl_prologue();
   const uint32_t T = a.torch_T, total = a.g.total;
   const bool aliased = a.x0b == a.x0;
@@ -291,7 +288,7 @@ __global__ void __launch_bounds__(kTorchThreads, 2) substep_torch_tma_kernel(con
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       mbar_init(&full[j], 1);
-      mbar_init(&empty[j], kTorchConsumers / 32);
+      mbar_init(&empty[j], kConsumers / 32);
     }
     mbar_fence_init();
   }
@@ -300,17 +297,17 @@ __global__ void __launch_bounds__(kTorchThreads, 2) substep_torch_tma_kernel(con
 
   // first element / length of sub-tile j of group (k, b)
   auto subtile = [&](uint32_t k, uint32_t b, int j, uint32_t& e0, uint32_t& len) {
-    const uint64_t e = (uint64_t)(4u * k + (uint32_t)j) * T + (uint64_t)b * kTorchG;
+    const uint64_t e = (uint64_t)(4u * k + (uint32_t)j) * T + (uint64_t)b * kG;
     if (e >= total) {
       e0 = 0;
       len = 0;
     } else {
       e0 = (uint32_t)e;
-      len = total - e0 < (uint32_t)kTorchG ? total - e0 : (uint32_t)kTorchG;
+      len = total - e0 < (uint32_t)kG ? total - e0 : (uint32_t)kG;
     }
   };
 
-  if (warp == kTorchConsumers / 32) {  // ---------------- producer ----------------
+  if (warp == kConsumers / 32) {  // ---------------- producer ----------------
     if (lane == 0) {
       const H* x0p = static_cast<const H*>(a.x0);
       const H* x0bp = static_cast<const H*>(a.x0b);
@@ -319,7 +316,7 @@ __global__ void __launch_bounds__(kTorchThreads, 2) substep_torch_tma_kernel(con
         const uint32_t k = grp / tg.groups_per_call, b = grp - k * tg.groups_per_call;
 #pragma unroll 1
         for (int j = 0; j < 4; ++j) {
-          mbar_wait(&empty[j], (it & 1u) ^ 1u);  // consumers have drained this slot (passes at once the first time)
+          mbar_wait_relaxed(&empty[j], (it & 1u) ^ 1u);  // consumers have drained this slot (passes at once the first time)
           uint32_t e0, len;
           subtile(k, b, j, e0, len);
           const uint32_t fb = len * 4u, hb = len * (uint32_t)sizeof(H);
@@ -359,11 +356,56 @@ __global__ void __launch_bounds__(kTorchThreads, 2) substep_torch_tma_kernel(con
     o0 += a.rng_state[1];
     o1 += a.rng_state[1];
   }
-  const uint32_t tid = threadIdx.x;  // 0..255: vector index inside every sub-tile
+  const uint32_t tid = threadIdx.x;  // vector index inside every sub-tile
+  // everything a thread does with one sub-tile once its data is in registers
+  auto finish = [&](uint32_t i, float (&x)[4], float (&x0)[4], float (&x0b)[4], const float (&y)[4],
+                    const float (&cp)[4], uchar4 mv, const float2 (&p1)[4], const float2 (&p2)[4], int jj) {
+    const uint32_t row = a.g.per_row.div(i);
+    RowCoef<kFirst, kNext> rc;
+    rc.load(a.table + (size_t)row * LP_TABLE_STRIDE);
+    if (a.use_cfg) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) cfg_combine(x0[q], x0b[q], a.cfg, a.cfg_big);
+    }
+    const bool known[4] = {mv.x != 0, mv.y != 0, mv.z != 0, mv.w != 0};
+    float cn[4];
+#pragma unroll
+    for (int q = 0; q < 4; q += 2) {   // two elements per FP32x2 op; bit-identical to substep_element
+      float xx[2] = {x[q], x[q + 1]}, h0[2] = {x0[q], x0[q + 1]}, h1[2] = {x0b[q], x0b[q + 1]}, cc[2];
+      const float yy[2] = {y[q], y[q + 1]}, pp[2] = {cp[q], cp[q + 1]};
+      const bool kk[2] = {known[q], known[q + 1]};
+      const float n1[2] = {jj ? p1[q].y : p1[q].x, jj ? p1[q + 1].y : p1[q + 1].x};
+      const float n2[2] = {jj ? p2[q].y : p2[q].x, jj ? p2[q + 1].y : p2[q + 1].x};
+      substep_element_x2<kFirst, kNext>(xx, h0, h1, yy, pp, kk, n1, n2, rc, cc);
+      x[q] = xx[0]; x[q + 1] = xx[1];
+      cn[q] = cc[0]; cn[q + 1] = cc[1];
+    }
+    *reinterpret_cast<float4*>(a.x + i) = make_float4(x[0], x[1], x[2], x[3]);
+    if (kNext || a.store_c) *reinterpret_cast<float4*>(a.c + i) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+  };
+  auto fetch = [&](const Slot& t, float (&x)[4], float (&x0)[4], float (&x0b)[4], float (&y)[4], float (&cp)[4],
+                   uchar4& mv) {
+    const float4 xv = reinterpret_cast<const float4*>(t.x)[tid];
+    lds_head4<H>(t.x0, tid, x0);
+    if (aliased) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) x0b[q] = x0[q];
+    } else {
+      lds_head4<H>(t.x0b, tid, x0b);
+    }
+    const float4 yv = reinterpret_cast<const float4*>(t.y)[tid];
+    const float4 cv = kFirst ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(t.c)[tid];
+    mv = reinterpret_cast<const uchar4*>(t.m)[tid];
+    x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
+    y[0] = yv.x; y[1] = yv.y; y[2] = yv.z; y[3] = yv.w;
+    cp[0] = cv.x; cp[1] = cv.y; cp[2] = cv.z; cp[3] = cv.w;
+  };
   uint32_t it = 0;
   for (uint32_t grp = blockIdx.x; grp < tg.n_groups; grp += gridDim.x, ++it) {
     const uint32_t k = grp / tg.groups_per_call, b = grp - k * tg.groups_per_call;
-    const uint32_t t0 = b * kTorchG + 4u * tid;  // my four Philox subsequences (torch threads)
+    const uint32_t t0 = b * kG + 4u * tid;  // my four Philox subsequences (torch threads)
+    // all four planes complete (every group but those at the very end of the tensor): no per-thread predicates
+    const bool whole = (uint64_t)(4u * k + 3u) * T + (uint64_t)(b + 1u) * kG <= total;
     uint4 r1[4], r2[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -374,59 +416,62 @@ __global__ void __launch_bounds__(kTorchThreads, 2) substep_torch_tma_kernel(con
     for (int h = 0; h < 2; ++h) {  // curand_normal4: planes 0,1 <- (x,y), planes 2,3 <- (z,w)
       float2 p1[4], p2[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        p1[i] = box_muller_curand(h ? r1[i].z : r1[i].x, h ? r1[i].w : r1[i].y);
-        p2[i] = kNext ? box_muller_curand(h ? r2[i].z : r2[i].x, h ? r2[i].w : r2[i].y) : make_float2(0.f, 0.f);
+      for (int i = 0; i < 4; i += 2) {   // two transforms per call: FP32x2 arithmetic, bit-identical to the scalar form
+        box_muller_curand_x2(h ? r1[i].z : r1[i].x, h ? r1[i].w : r1[i].y, h ? r1[i + 1].z : r1[i + 1].x,
+                             h ? r1[i + 1].w : r1[i + 1].y, p1[i], p1[i + 1]);
+        if (kNext) {
+          box_muller_curand_x2(h ? r2[i].z : r2[i].x, h ? r2[i].w : r2[i].y, h ? r2[i + 1].z : r2[i + 1].x,
+                               h ? r2[i + 1].w : r2[i + 1].y, p2[i], p2[i + 1]);
+        } else {
+          p2[i] = p2[i + 1] = make_float2(0.f, 0.f);
+        }
       }
 #pragma unroll
       for (int jj = 0; jj < 2; ++jj) {
         const int j = 2 * h + jj;
-        uint32_t e0, len;
-        subtile(k, b, j, e0, len);
-        mbar_wait(&full[j], it & 1u);
-        const bool active = 4u * tid < len;
         float x[4], x0[4], x0b[4], y[4], cp[4];
         uchar4 mv = make_uchar4(0, 0, 0, 0);
-        if (active) {
-          const Slot& t = slot[j];
-          const float4 xv = reinterpret_cast<const float4*>(t.x)[tid];
-          lds_head4<H>(t.x0, tid, x0);
-          if (aliased) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) x0b[q] = x0[q];
-          } else {
-            lds_head4<H>(t.x0b, tid, x0b);
-          }
-          const float4 yv = reinterpret_cast<const float4*>(t.y)[tid];
-          const float4 cv = kFirst ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<const float4*>(t.c)[tid];
-          mv = reinterpret_cast<const uchar4*>(t.m)[tid];
-          x[0] = xv.x; x[1] = xv.y; x[2] = xv.z; x[3] = xv.w;
-          y[0] = yv.x; y[1] = yv.y; y[2] = yv.z; y[3] = yv.w;
-          cp[0] = cv.x; cp[1] = cv.y; cp[2] = cv.z; cp[3] = cv.w;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[j]);  // this warp's reads of slot j are in registers: let it refill
-        if (active) {
-          const uint32_t i = e0 + 4u * tid;
-          const uint32_t row = a.g.per_row.div(i);
-          RowCoef<kFirst, kNext> rc;
-          rc.load(a.table + (size_t)row * LP_TABLE_STRIDE);
-          if (a.use_cfg) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) cfg_combine(x0[q], x0b[q], a.cfg, a.cfg_big);
-          }
-          const bool known[4] = {mv.x != 0, mv.y != 0, mv.z != 0, mv.w != 0};
-          float cn[4], te[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            substep_element<kFirst, kNext, false>(x[q], x0[q], x0b[q], y[q], cp[q], known[q],
-                                                  jj ? p1[q].y : p1[q].x, jj ? p2[q].y : p2[q].x, rc, cn[q], te[q]);
-          *reinterpret_cast<float4*>(a.x + i) = make_float4(x[0], x[1], x[2], x[3]);
-          if (kNext || a.store_c) *reinterpret_cast<float4*>(a.c + i) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+        mbar_wait(&full[j], it & 1u);
+        if (whole) {
+          fetch(slot[j], x, x0, x0b, y, cp, mv);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[j]);  // this warp's reads of slot j are in registers: let it refill
+          finish((4u * k + (uint32_t)j) * T + t0, x, x0, x0b, y, cp, mv, p1, p2, jj);
+        } else {
+          uint32_t e0, len;
+          subtile(k, b, j, e0, len);
+          const bool active = 4u * tid < len;
+          if (active) fetch(slot[j], x, x0, x0b, y, cp, mv);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[j]);
+          if (active) finish(e0 + 4u * tid, x, x0, x0b, y, cp, mv, p1, p2, jj);
         }
       }
     }
   }
+}
+
+// launch geometries: <kG, CTAs per SM>.  The default (1024, 2) keeps two independent CTAs per SM; (2048, 1) trades
+// that for a higher register ceiling per thread (more Box-Muller chains in flight); _r112 is (1024, 2) with the
+// register ceiling spelled out instead of derived from the launch bounds.
+template <typename H, bool kFirst, bool kNext>
+__global__ void __launch_bounds__(1024 / 4 + 32, 2) substep_torch_tma_kernel(const SubstepArgs a, const TorchTmaGeom tg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[4], empty[4];
+  torch_tma_body<H, kFirst, kNext, 1024>(a, tg, smem_raw, full, empty);
+}
+template <typename H, bool kFirst, bool kNext>
+__global__ void __maxnreg__(112)
+    substep_torch_tma_kernel_r112(const SubstepArgs a, const TorchTmaGeom tg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[4], empty[4];
+  torch_tma_body<H, kFirst, kNext, 1024>(a, tg, smem_raw, full, empty);
+}
+template <typename H, bool kFirst, bool kNext>
+__global__ void __maxnreg__(120) substep_torch_tma_kernel_g2048(const SubstepArgs a, const TorchTmaGeom tg) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full[4], empty[4];
+  torch_tma_body<H, kFirst, kNext, 2048>(a, tg, smem_raw, full, empty);
 }
 
 // ---- TORCH, 128-bit LDG path ----------------------------------------------------------------------
@@ -534,7 +579,8 @@ template <typename H, bool kFirst, bool kNext, bool kMerge, int kTile, int kStag
 int launch_substep_tma_cfg(const SubstepArgs& a, cudaStream_t s) {
   const int dev = current_device();
   const size_t smem = sizeof(TmaStage<H, kTile>) * kStages;
-  ensure_dynamic_smem(substep_tma_kernel<H, kFirst, kNext, kMerge, kTile, kStages, kMinBlocks>, smem, dev);
+  static bool configured[kMaxDevices] = {};  // per instantiation of this launcher
+  ensure_dynamic_smem(substep_tma_kernel<H, kFirst, kNext, kMerge, kTile, kStages, kMinBlocks>, smem, dev, configured);
   TileGeom tg;
   tg.channels = a.g.per_row.d / a.g.spatial.d;
   tg.tiles_per_channel = (a.g.spatial.d + kTile - 1) / kTile;
@@ -598,14 +644,27 @@ int launch_substep_vec(const SubstepArgs& a, bool first, bool next, bool merge, 
 template <typename H, bool kFirst, bool kNext>
 int launch_torch_tma(const SubstepArgs& a, uint32_t calls, cudaStream_t s) {
   const int dev = current_device();
-  const size_t smem = sizeof(TorchSlot<H>) * 4;
-  ensure_dynamic_smem(substep_torch_tma_kernel<H, kFirst, kNext>, smem, dev);
+  const int variant = (sizeof(H) == 4 && !kFirst && kNext) ? g_opt_tma : 1;   // alternatives: steady fp32 kernel only
+  const int kG = variant == 7 ? 2048 : 1024;
+  const size_t smem = (variant == 7 ? sizeof(TorchSlot<H, 2048>) : sizeof(TorchSlot<H, 1024>)) * 4;
   TorchTmaGeom tg;
-  tg.groups_per_call = a.torch_T / kTorchG;
+  tg.groups_per_call = a.torch_T / kG;
   tg.n_groups = calls * tg.groups_per_call;
-  unsigned grid = (unsigned)device_info(dev).sms * 2u;
+  unsigned grid = (unsigned)device_info(dev).sms * (variant == 7 ? 1u : 2u);
   if (grid > tg.n_groups) grid = tg.n_groups;
-  launch_kernel_ex(substep_torch_tma_kernel<H, kFirst, kNext>, dim3(grid), dim3(kTorchThreads), smem, s, a, tg);
+  if (variant == 7) {
+    static bool configured[kMaxDevices] = {};
+    ensure_dynamic_smem(substep_torch_tma_kernel_g2048<H, kFirst, kNext>, smem, dev, configured);
+    launch_kernel_ex(substep_torch_tma_kernel_g2048<H, kFirst, kNext>, dim3(grid), dim3(2048 / 4 + 32), smem, s, a, tg);
+  } else if (variant == 6) {
+    static bool configured[kMaxDevices] = {};
+    ensure_dynamic_smem(substep_torch_tma_kernel_r112<H, kFirst, kNext>, smem, dev, configured);
+    launch_kernel_ex(substep_torch_tma_kernel_r112<H, kFirst, kNext>, dim3(grid), dim3(1024 / 4 + 32), smem, s, a, tg);
+  } else {
+    static bool configured[kMaxDevices] = {};
+    ensure_dynamic_smem(substep_torch_tma_kernel<H, kFirst, kNext>, smem, dev, configured);
+    launch_kernel_ex(substep_torch_tma_kernel<H, kFirst, kNext>, dim3(grid), dim3(1024 / 4 + 32), smem, s, a, tg);
+  }
   return check_launch();
 }
 
@@ -617,7 +676,7 @@ int substep_dispatch(SubstepArgs& a, const lp_rng* rng, bool f, bool n, bool mer
     a.torch_T = (uint32_t)(grid * 256);
     const unsigned gb = (unsigned)grid;
     const uint64_t calls = ((uint64_t)a.g.total + 4ull * a.torch_T - 1) / (4ull * a.torch_T);
-    if (v4 && tma_eligible(a) && a.torch_T % kTorchG == 0 && a.g.spatial.d >= 64 && calls <= 0xffffffffull / 4) {
+    if (v4 && tma_eligible(a) && a.torch_T % 2048 == 0 && a.g.spatial.d >= 64 && calls <= 0xffffffffull / 4) {
       if (f && n) return launch_torch_tma<H, true, true>(a, (uint32_t)calls, s);
       if (f) return launch_torch_tma<H, true, false>(a, (uint32_t)calls, s);
       if (n) return launch_torch_tma<H, false, true>(a, (uint32_t)calls, s);

@@ -71,7 +71,7 @@ def _wrap_distance_fn(fn: Optional[Callable[..., Any]]):
 
 class EarlyStopper:
     def __init__(self, *, threshold, threshold_eff, patience_eff, mask, ring, w_inpaint, w_ring, dims, distance_fn,
-                 trace, bench_ids, abt_val, device):
+                 trace, bench_ids, abt_val, device, reduce=None):
         self.enabled = True
         self.threshold = float(threshold)
         self.threshold_eff = float(threshold_eff)
@@ -86,6 +86,9 @@ class EarlyStopper:
         self.x0_anchor: Optional[torch.Tensor] = None
         self._dist_wrapper = _wrap_distance_fn(distance_fn)
         self._sums = torch.zeros(2, dtype=torch.float64, device=device)
+        # a latent sharded across ranks (frame_shard.py): the two masked sums are the ONLY cross-shard quantity of the
+        # whole hot path; `reduce(tensor)` sums them over the shards in place (one all_reduce of 2 doubles per check)
+        self._reduce = reduce
         self._bufs = [None, None]
         self._turn = 0
         self.reads = 0  # host read-backs issued (one per statistics kernel)
@@ -101,15 +104,22 @@ class EarlyStopper:
             self._bufs[k] = torch.empty_like(like)
         return self._bufs[k]
 
-    def _stats(self, a: torch.Tensor, b: torch.Tensor, table=None):
-        """(weighted MSE over the inpaint region, over the ring or None) -- earlystop.py:51-55."""
+    def _local_sums(self, a: torch.Tensor, b: torch.Tensor, table=None) -> torch.Tensor:
+        """This shard's two masked sums of squared differences, on the device (lp_stop_stats_f32)."""
         lib = _native.load()
         rc = lib.lp_stop_stats_f32(_P(a.data_ptr()), _P(b.data_ptr()), _P(self.mask.data_ptr()),
                                    _P(self.ring.data_ptr()) if self.ring is not None else None,
                                    _P(table.data_ptr()) if table is not None else None, C.byref(self.dims),
                                    _P(self._sums.data_ptr()), _P(torch.cuda.current_stream(a.device).cuda_stream))
         _native.check(rc, "lp_stop_stats_f32")
-        s_in, s_ring = self._sums.tolist()  # the one host read-back of this check
+        return self._sums
+
+    def _stats(self, a: torch.Tensor, b: torch.Tensor, table=None):
+        """(weighted MSE over the inpaint region, over the ring or None) -- earlystop.py:51-55."""
+        sums = self._local_sums(a, b, table)
+        if self._reduce is not None:
+            self._reduce(sums)
+        s_in, s_ring = sums.tolist()  # the one host read-back of this check
         self.reads += 1
         d_in = s_in / (self.w_inpaint + 1e-12)
         d_ring = None if self.ring is None else s_ring / (self.w_ring + 1e-12)
@@ -178,7 +188,7 @@ class EarlyStopper:
 
 
 def make_stopper(*, model_options, default_threshold, default_patience, default_distance_fn, packed_mask, like,
-                 abt_mean: float, dims) -> Optional[EarlyStopper]:
+                 abt_mean: float, dims, reduce=None) -> Optional[EarlyStopper]:
     """LanPaintEarlyStopper.from_options (earlystop.py:63-151) over a packed uint8 mask."""
     semantic = model_options.get("lanpaint_semantic_stop") if isinstance(model_options, dict) else None
     threshold = float(default_threshold)
@@ -202,11 +212,15 @@ def make_stopper(*, model_options, default_threshold, default_patience, default_
         return None
     m = packed_mask.data
     channels = like.shape[1] if packed_mask.channel_stride == 0 else 1
-    w_in = float((m == 0).sum().item()) * channels
+    ring = boundary_ring(m) if like.dim() == 4 else None
+    counts = torch.stack([(m == 0).sum(), ring.sum() if ring is not None else m.new_zeros(()).sum()]).to(torch.float64)
+    if reduce is not None:   # weights of the whole latent, not of this shard
+        reduce(counts)
+    n_in, n_ring = counts.tolist()
+    w_in = float(n_in) * channels
     if w_in < 1e-6:
         return None
-    ring = boundary_ring(m) if like.dim() == 4 else None
-    w_ring = None if ring is None else float(ring.sum().item()) * channels
+    w_ring = None if ring is None else float(n_ring) * channels
     trace = model_options.get("lanpaint_semantic_trace") if isinstance(model_options, dict) else None
     ids = (None, None, None)
     if isinstance(trace, list) and isinstance(model_options, dict):
@@ -214,4 +228,4 @@ def make_stopper(*, model_options, default_threshold, default_patience, default_
                model_options.get("bench_timestep"))
     return EarlyStopper(threshold=threshold, threshold_eff=threshold_eff, patience_eff=max(1, patience) + 1, mask=m,
                         ring=ring, w_inpaint=w_in, w_ring=w_ring, dims=dims, distance_fn=distance_fn, trace=trace,
-                        bench_ids=ids, abt_val=float(abt_mean), device=like.device)
+                        bench_ids=ids, abt_val=float(abt_mean), device=like.device, reduce=reduce)

@@ -256,6 +256,7 @@ class LanPaint:
         self._av_cache = _IdentityCache()
         self._av_mask_cache = _IdentityCache()
         self._ws = {}
+        self.stats_reduce = None  # frame_shard.py: sums the early stopper's two statistics over the shards of a latent
         self.kernel_timer = None  # set to a list to collect (flags, start_event, stop_event) per substep launch
         _native.load()  # fail at construction, loudly, if the CUDA library is absent
 
@@ -700,7 +701,7 @@ class LanPaint:
         return make_stopper(model_options=model_options, default_threshold=self.early_stop_threshold,
                             default_patience=self.early_stop_patience, default_distance_fn=self.early_stop_hook,
                             packed_mask=pm, like=like, abt_mean=float(np.float32(abt_h.astype(np.float32).mean())),
-                            dims=dims)
+                            dims=dims, reduce=self.stats_reduce)
 
     # ---- the reference's lower-level entry point, un-fused ------------------------------------------
     def langevin_dynamics(self, x_t, score, mask, step_size, current_times, sigma_x=1, sigma_y=0, args=None):

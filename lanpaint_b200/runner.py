@@ -202,14 +202,18 @@ def time_steady_substep(engine, latent_image: torch.Tensor, mask, sigma: float, 
     P = C.c_void_p
     stream = P(torch.cuda.current_stream(dev).cuda_stream)
 
+    from .engine import _heads
+    for o in sets:   # heads in whatever dtype the model returns (fp32 / bf16 / fp16)
+        o["heads"], o["keep"] = _heads(o["x0"], o["x0b"], o["x"])
+
     def burst():
         for k in range(launches):
             o = sets[k % len(sets)]
             r = plan.rng_struct(1 if merge else 2)
-            rc = lib.lp_substep_f32(P(o["x"].data_ptr()), P(o["x0"].data_ptr()), P(o["x0b"].data_ptr()),
-                                    P(o["y"].data_ptr()), P(o["m"].data_ptr()), P(o["c"].data_ptr()), None, None,
-                                    P(tab.data_ptr()), C.byref(dims), C.byref(r), flags, stream)
-            _native.check(rc, "lp_substep_f32")
+            rc = lib.lp_substep(P(o["x"].data_ptr()), C.byref(o["heads"]), P(o["y"].data_ptr()), P(o["m"].data_ptr()),
+                                P(o["c"].data_ptr()), None, None, P(tab.data_ptr()), C.byref(dims), C.byref(r), flags,
+                                stream)
+            _native.check(rc, "lp_substep")
 
     for _ in range(3):
         burst()
@@ -283,9 +287,10 @@ class GraphedJob:
             self.active.append(st.n_inner if mean_half_dt(abt, hyper) > 0.0 else 0)
         # draws consumed before outer step i (1 for sub-step 0, 2 for each later one): lets every outer step be
         # captured on its own against ONE {seed, base} block that is refreshed once per job
+        merged = engine.rng == "philox" and engine.merge_noise   # a fused launch then draws ONE normal, not two
         self.draws_before = [0]
         for n in self.active:
-            self.draws_before.append(self.draws_before[-1] + (2 * n - 1 if n > 0 else 0))
+            self.draws_before.append(self.draws_before[-1] + (0 if n <= 0 else (n if merged else 2 * n - 1)))
         self.tables = torch.from_numpy(np.stack(tabs)).to(dev)
         self.t_model = torch.from_numpy(np.stack(tms).astype(np.float32)).to(dev)
         self.sigma = torch.from_numpy(np.stack(sgs).astype(np.float32)).to(dev)
@@ -348,12 +353,13 @@ class GraphedJob:
         eng = self.engine
         counts = (eng.launches, eng.model_calls, eng.substeps_done)
         timer, eng.kernel_timer = eng.kernel_timer, None
+        plan = self._relative_plan()   # built BEFORE capture begins: reading the generator's offset is not capturable
         try:
             if warm:
                 side = torch.cuda.Stream(device=self.device)
                 side.wait_stream(torch.cuda.current_stream(self.device))
                 with torch.cuda.stream(side):
-                    fn(self._relative_plan())
+                    fn(plan)
                 torch.cuda.current_stream(self.device).wait_stream(side)
                 eng.launches, eng.model_calls, eng.substeps_done = counts
             graph = torch.cuda.CUDAGraph()
@@ -366,7 +372,7 @@ class GraphedJob:
                     self.l2_window = nbytes
             cap_stream.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.graph(graph, stream=cap_stream):
-                fn(self._relative_plan())
+                fn(plan)
             if self.l2_window:
                 lib.lp_l2_persist_clear(cap)
         finally:
@@ -388,7 +394,10 @@ class GraphedJob:
         import numpy as np
         from .engine import PackedMask, pack_mask
         self.y.copy_(latent_image, non_blocking=True)
-        self.noise.copy_(noise, non_blocking=True)
+        if noise is None:   # serving hosts that do not need ComfyUI's CPU noise image: draw it on the device
+            self.noise.normal_()
+        else:
+            self.noise.copy_(noise, non_blocking=True)
         if x_init is not None:
             self.x.copy_(x_init, non_blocking=True)
         pm = mask if isinstance(mask, PackedMask) else pack_mask(mask, self.x)

@@ -48,10 +48,23 @@ class ModelSamplingEPS:
 
 
 class ModelSamplingCONST:
-    """Rectified-flow parameterisation (x_t = sigma*noise + (1-sigma)*x_0)."""
+    """Rectified-flow parameterisation (x_t = sigma*noise + (1-sigma)*x_0) with ComfyUI's time shift:
+    sigma(t) = shift*t / (1 + (shift-1)*t), tabulated at t = 1/1000 .. 1 (ModelSamplingDiscreteFlow)."""
 
-    sigma_min, sigma_max = 0.0, 1.0
     noise_scale = 1.0
+
+    def __init__(self, shift: float = 1.0, timesteps: int = 1000):
+        self.shift = float(shift)
+        t = torch.arange(1, timesteps + 1, dtype=torch.float32) / timesteps
+        self.sigmas = self.shift * t / (1 + (self.shift - 1) * t)
+
+    @property
+    def sigma_min(self):
+        return self.sigmas[0]
+
+    @property
+    def sigma_max(self):
+        return self.sigmas[-1]
 
     def noise_scaling(self, sigma, noise, latent_image, max_denoise=False):
         sigma = sigma.view(sigma.shape[:1] + (1,) * (noise.ndim - 1)) if sigma.ndim <= 1 else sigma
@@ -65,10 +78,11 @@ class ModelSamplingCONST:
 class BaseModel:
     """`denoiser(x, sigma, cond) -> x0 prediction` wrapped with ComfyUI's BaseModel members."""
 
-    def __init__(self, denoiser: Callable, model_type=ModelType.EPS, latent_channels: int = 4):
+    def __init__(self, denoiser: Callable, model_type=ModelType.EPS, latent_channels: int = 4, shift: float = 1.0):
         self.diffusion_model = denoiser
         self.model_type = model_type
-        self.model_sampling = ModelSamplingCONST() if model_type in (ModelType.FLUX, ModelType.FLOW) else ModelSamplingEPS()
+        self.model_sampling = (ModelSamplingCONST(shift) if model_type in (ModelType.FLUX, ModelType.FLOW)
+                               else ModelSamplingEPS())
         self.latent_channels = latent_channels
 
     def apply_model(self, x, t, c=None, **kwargs):
@@ -343,9 +357,15 @@ def get_sigmas_karras(n, sigma_min, sigma_max, rho=7.0, device="cpu"):
 
 
 def simple_scheduler(model_sampling, steps):
-    hi, lo = float(model_sampling.sigma_max), max(float(model_sampling.sigma_min), 1e-3)
-    s = torch.linspace(hi, lo, steps) if hi <= 1.0 else torch.exp(torch.linspace(math.log(hi), math.log(lo), steps))
-    return torch.cat([s, s.new_zeros([1])])
+    """comfy.samplers.simple_scheduler: every (len/steps)-th entry of the model's sigma table, from the top."""
+    table = getattr(model_sampling, "sigmas", None)
+    if table is None:   # EPS stand-in has no table: log-spaced between its extremes
+        hi, lo = float(model_sampling.sigma_max), max(float(model_sampling.sigma_min), 1e-3)
+        s = torch.exp(torch.linspace(math.log(hi), math.log(lo), steps))
+        return torch.cat([s, s.new_zeros([1])])
+    ss = len(table) / steps
+    sigs = [float(table[-(1 + int(x * ss))]) for x in range(steps)] + [0.0]
+    return torch.FloatTensor(sigs)
 
 
 class KSampler:

@@ -34,6 +34,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_native.Hyper) == 40
     assert C.sizeof(_native.Dims) == 48
     assert C.sizeof(_native.Rng) == 56
+    assert C.sizeof(_native.Heads) == 32 and _native.Heads.dtype.offset == 16 and _native.Heads.cfg.offset == 24
     assert _native.Rng.seed.offset == 24 and _native.Rng.state.offset == 48
     assert _native.TABLE_STRIDE == 32
 

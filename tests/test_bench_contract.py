@@ -21,7 +21,8 @@ def test_reference_arm_prints_one_contract_line():
     assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["config"]["workload"].startswith("sdxl_1024_inpaint") and d["config"]["substeps_per_request"] == 53
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] > 0 and "sample" in cb
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] > 0 and "sample" in cb
+    assert d["config"]["reference_requests"] == 2
     assert d["e2e"] == {"value": d["value"], "unit": "sub-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -715,6 +715,20 @@ def test_tma_staged_variant_is_bit_identical(cuda_device):
         lib.lp_set_option(b"tma", 1)   # the default
 
 
+def test_packed_box_muller_is_bit_identical_to_curands(cuda_device):
+    """The torch-stream TMA kernel computes cuRAND's Box-Muller two at a time in FP32x2 (FFMA2) arithmetic with
+    CUDA's logf / sqrtf specialised to the argument range.  Device self test: 2^28 pseudo-random input quadruples
+    plus every combination of the extreme inputs, bitwise against the scalar cuRAND form."""
+    from lanpaint_b200 import _native
+    lib = _native.load()
+    bad = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+    for seed in (1, 0xDEADBEEFCAFE):
+        rc = lib.lp_selftest_box_muller(1 << 28, seed, C.c_void_p(bad.data_ptr()),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        assert int(bad.item()) == 0
+
+
 def test_torch_stream_tma_variant_is_bit_identical(cuda_device):
     """The seed-exact stream at HBM-bound sizes runs substep_torch_tma_kernel (producer warp + cp.async.bulk slots,
     4 Philox subsequences per thread).  It must reproduce the LDG torch kernels bit for bit -- same randn stream,
@@ -862,8 +876,9 @@ def test_half_precision_heads_are_read_in_kernel(dtype, rng_mode, cuda_device):
         class HalfOracle(O.PointwiseDenoiser):
             def __call__(self, xx, t, model_options=None, seed=None):
                 return tuple(h.to(dtype) for h in super().__call__(xx, t))
-        want_out, want_x = O.outer_step(HalfOracle(O.VESampling()), x.cpu().clone(), y.cpu(), noise.cpu(), sig,
-                                        m.cpu().expand(shape), O.times_from_sigma(sig, False), hp, n_steps=n, draw=tape)
+        # the oracle runs on the device too: its network must round the very same fp32 values to half precision
+        want_out, want_x = O.outer_step(HalfOracle(O.VESampling()), x.clone(), y, noise, sig.to(dev), m.expand(shape),
+                                        O.times_from_sigma(sig.to(dev), False), hp, n_steps=n, draw=tape)
         eng = _engine(HalfOracle(O.VESampling()), dict(n_steps=n), rng=NoiseTape([d.to(dev) for d in tape.recorded]))
         xx = x.clone()
         out = eng(xx, y, noise, sig, m, times, None, 0, n_steps=n)
