@@ -107,7 +107,7 @@ def test_sharded_stopper_takes_the_unsharded_decisions_over_gloo():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("threshold", [0.0, 0.02])
+@pytest.mark.parametrize("threshold", [0.0, 50.0])
 def test_frame_sharded_run_equals_unsharded_run(threshold, cuda_device):
     """Two shards (threads of this process, one GPU) vs the whole sample, same noise tape: bit-equal latents,
     identical early-stop decisions, and -- with the stopper off -- no collective at all."""
