@@ -155,6 +155,6 @@ def test_frame_sharded_run_equals_unsharded_run(threshold, cuda_device):
         assert done_whole < sched.substeps and len(tr_whole) > 0          # the stopper did cut sub-steps
         for r in (0, 1):
             assert [(a, b) for a, b, _ in out[r][1]] == [(a, b) for a, b, _ in tr_whole]
-            assert [d for _, _, d in out[r][1]] == pytest.approx([d for _, _, d in tr_whole], rel=1e-9)
+            assert [d for _, _, d in out[r][1]] == pytest.approx([d for _, _, d in tr_whole], rel=1e-6)   # fp32 partial-sum order
     else:
         assert done_whole == sched.substeps
