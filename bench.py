@@ -492,6 +492,33 @@ def run_b200(args):
                                              "what": "two-head synthetic network (73 network kernels per request instead of "
                                                      "146), rng=philox, runner.GraphedJob: the configuration of BENCH_r01.value"}
         del job, eng
+        if world == 1:   # batch-size sweep of that configuration (R = 256: every byte from HBM; small R: launch-bound)
+            sweep = []
+            for r in (1, 8, 32, 64, 256):
+                s_r = HostSchedule(karras_sigmas(N_OUTER), r, N_INNER)
+                g_r = torch.Generator().manual_seed(5)
+                y_r = torch.randn((r,) + SHAPE, generator=g_r).to(dev)
+                n_r = torch.randn((r,) + SHAPE, generator=g_r).to(dev)
+                p_r = pack_mask((torch.rand((r, 1) + SHAPE[1:], generator=g_r) < 0.5).to(dev), y_r)
+                e_r = LanPaint(SynthDenoiser(VESampling()), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0, StepSize=0.2,
+                               MinStepFrac=1.0, rng="philox", batched_replace="per_sample")
+                j_r = GraphedJob(e_r, s_r, (r,) + SHAPE, dev)
+                for _ in range(3):
+                    j_r.run(y_r, n_r, p_r)
+                torch.cuda.synchronize()
+                reps = 40 if r <= 64 else 12
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                for _ in range(reps):
+                    j_r.run(y_r, n_r, p_r)
+                a1.record()
+                torch.cuda.synchronize()
+                t_r = a0.elapsed_time(a1) / reps
+                sweep.append({"requests_per_gpu": r, "ms_per_job": t_r, "value": r * s_r.substeps / (t_r * 1e-3),
+                              "us_per_graph_node": 1e3 * t_r / (j_r.launches + j_r.model_calls)})
+                del j_r, e_r, y_r, n_r, p_r
+                torch.cuda.empty_cache()
+            serving["round1_headline_config"]["sweep"] = sweep
         ref_ms = serving[args.rng]["ms_per_job"]
         serving["node_api_over_graphed_job"] = main["ms_per_job_device"] / ref_ms
         # host tensors in, host result out through the same object, two batches in flight, uint8 mask, noise drawn on
@@ -710,12 +737,15 @@ def run_frame_shard(group, dev, args):
     frames split over the ranks; the update kernels need no exchange, the early stopper's two masked sums are the
     only cross-shard quantity (one all_reduce of 2 doubles per check)."""
     from lanpaint_b200.frame_shard import FrameShardedRun
-    try:
-        run = FrameShardedRun(group, dev, latent=(16, 21, 80, 45), n_inner=N_INNER, steps=N_OUTER, shift=3.0,
-                              early_stop_threshold=args.frame_shard_threshold)
-        return run.bench(jobs=10)
-    except Exception as e:
-        return {"error": f"{type(e).__name__}: {e}"}
+    out = {}
+    for key, thr in (("stopper_off", 0.0), ("stopper_on", args.frame_shard_threshold)):
+        try:
+            run = FrameShardedRun(group, dev, latent=(16, 21, 80, 45), n_inner=N_INNER, steps=N_OUTER, shift=3.0,
+                                  early_stop_threshold=thr)
+            out[key] = run.bench(jobs=10 if thr <= 0 else 3)
+        except Exception as e:
+            out[key] = {"error": f"{type(e).__name__}: {e}"}
+    return out
 
 
 def main():
@@ -735,8 +765,8 @@ def main():
     ap.add_argument("--no-configs", dest="configs", action="store_false", help="skip the BASELINE configuration records")
     ap.add_argument("--no-kernel-timer", dest="kernel_timer", action="store_false")
     ap.add_argument("--no-frame-shard", dest="frame_shard", action="store_false")
-    ap.add_argument("--frame-shard-threshold", type=float, default=0.0,
-                    help="> 0: run the frame-sharded record with the early stopper on (one all_reduce per check)")
+    ap.add_argument("--frame-shard-threshold", type=float, default=0.05,
+                    help="InnerThreshold of the frame-sharded record that runs with the early stopper on")
     ap.add_argument("--mask", default="random", choices=["random", "blob"],
                     help="random 50%% per site (SURVEY 8d, default) | one centred hole of about the same area")
     args = ap.parse_args()

@@ -288,7 +288,7 @@ __device__ __forceinline__ void torch_tma_body(const SubstepArgs& a, const Torch
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       mbar_init(&full[j], 1);
-      mbar_init(&empty[j], kConsumers / 32);
+      mbar_init(&empty[j], kConsumers);
     }
     mbar_fence_init();
   }
@@ -400,6 +400,10 @@ __device__ __forceinline__ void torch_tma_body(const SubstepArgs& a, const Torch
     y[0] = yv.x; y[1] = yv.y; y[2] = yv.z; y[3] = yv.w;
     cp[0] = cv.x; cp[1] = cv.y; cp[2] = cv.z; cp[3] = cv.w;
   };
+  // every consumer THREAD releases the slot itself once its reads are in registers.  (One arrive per warp after a
+  // __syncwarp() measured the same 44 us, but compute-sanitizer's racecheck cannot follow that form: 11 hazards
+  // against the producer's next cp.async.bulk; with per-thread arrives it reports none -- profiles/r02_sanitizer_*.)
+  auto release = [&](int j) { mbar_arrive(&empty[j]); };
   uint32_t it = 0;
   for (uint32_t grp = blockIdx.x; grp < tg.n_groups; grp += gridDim.x, ++it) {
     const uint32_t k = grp / tg.groups_per_call, b = grp - k * tg.groups_per_call;
@@ -434,16 +438,14 @@ __device__ __forceinline__ void torch_tma_body(const SubstepArgs& a, const Torch
         mbar_wait(&full[j], it & 1u);
         if (whole) {
           fetch(slot[j], x, x0, x0b, y, cp, mv);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[j]);  // this warp's reads of slot j are in registers: let it refill
+          release(j);  // this warp's reads of slot j are in registers: let it refill
           finish((4u * k + (uint32_t)j) * T + t0, x, x0, x0b, y, cp, mv, p1, p2, jj);
         } else {
           uint32_t e0, len;
           subtile(k, b, j, e0, len);
           const bool active = 4u * tid < len;
           if (active) fetch(slot[j], x, x0, x0b, y, cp, mv);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[j]);
+          release(j);
           if (active) finish(e0 + 4u * tid, x, x0, x0b, y, cp, mv, p1, p2, jj);
         }
       }
