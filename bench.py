@@ -331,9 +331,18 @@ class NodeWorkload:
         self.last_out = out["samples"]
         return wall, e0.elapsed_time(e1)
 
-    def warm(self, n=3):
-        for _ in range(n):     # eager -> capture -> replay
+    def warm(self, n=8):
+        """eager -> capture (per-step graphs) -> replay -> [short job: capture the whole-job graph] -> replay;
+        stops once two consecutive calls were pure replays of the same kind."""
+        modes = []
+        for _ in range(n):
+            job = self.N.LAST_RUN.get("job")
+            before = job.captures if job is not None else -1
             self.call()
+            job = self.N.LAST_RUN.get("job")
+            modes.append((self.N.LAST_RUN["mode"], job is not None and job.captures == before))
+            if len(modes) >= 2 and modes[-1] == modes[-2] and modes[-1][1] and modes[-1][0] != "eager":
+                break
         return self.N.LAST_RUN["mode"]
 
     def prepare_noise_ms(self, reps=3):
@@ -393,7 +402,7 @@ def run_b200(args):
         """steps x jobs node calls: device time of the sampler loops (sum, max over ranks) and wall time."""
         wl = NodeWorkload(spec, dev, rng, seed=seed)
         wl.net.coef = tuple(weights.tolist())
-        wl.warm(3)
+        wl.warm()
         for _ in range(warm_steps * jobs):
             wl.call()
         group.barrier()

@@ -345,7 +345,7 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
         # NB: while the patch is active this function is installed on comfy.samplers.KSAMPLER itself, so `self`
         # is ComfyUI's class, not this subclass: helpers are reached through the class, never through `self`
         extra_args["denoise_mask"] = denoise_mask
-        LAST_RUN.update(mode=None, fused=False, job=None, events=None)
+        LAST_RUN.update(mode=None, fused=False, job=None, events=None, events_call=None)
         model_k = KSamplerX0Inpaint(model_wrap, sigmas)
         model_k.latent_image = latent_image
         if self.inpaint_options.get("random", False):
@@ -415,7 +415,10 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
         self.last_engine = engine
         if timing is not None:
             timing[1].record()
-            LAST_RUN["events"] = timing
+            job = LAST_RUN.get("job")
+            # fused loop: the events GraphedJob recorded around the loop itself (inputs resident in its buffers)
+            LAST_RUN["events"] = job.last_events if (job is not None and job.last_events is not None) else timing
+            LAST_RUN["events_call"] = timing    # whole KSAMPLER.sample body, host-side preparation included
         return base.model_sampling.inverse_noise_scaling(sigmas[-1], samples)
 
     # ---- plain Euler: the sampler loop as one launch sequence ---------------------------------------
@@ -459,17 +462,37 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
             if entry is not None:
                 entry.job = job
         job.model_options, job.seed = model_options, seed
+        job.timing = bool(opts.get("timing"))
         pm = model_k._latent_mask(denoise_mask, x_init)
         runs = entry.runs if entry is not None else 0
         after = int(opts.get("graph_after", 1))
         captures = job.captures
         if not use_graph or entry is None or entry.graph_failed or runs < after:
             mode = "eager"
+        elif callback is None:
+            mode = "job"
         else:
-            mode = "steps" if callback is not None else "job"
+            # ComfyUI always passes a callback (progress bar / preview / interrupt check).  One graph per outer step
+            # keeps it live -- right for a real network, where a step takes long enough to watch.  When the eager
+            # job of this configuration took only a few milliseconds nobody can watch anything: the whole job runs
+            # as ONE graph, each outer step keeps its denoised latent, and the callbacks run in order right after.
+            dev_ms = None      # device time of this configuration's previous job (the very first one of a process
+            if entry.eager_events is not None:   # also pays CUDA's lazy module loading and is re-measured)
+                dev_ms = entry.eager_events[0].elapsed_time(entry.eager_events[1])
+            deferred = (opts.get("deferred_callbacks", True) and dev_ms is not None
+                        and dev_ms <= float(opts.get("deferred_max_ms", 20.0))
+                        and job.per_step_bytes() <= int(opts.get("deferred_max_bytes", 1 << 30)))
+            mode = "job" if deferred else "steps"
+        timing = None
+        if entry is not None:
+            timing = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            timing[0].record()
         try:
             out = job.run(latent_image, model_k.noise, pm, x_init=x_init, callback=callback, mode=mode,
                           warm=after <= 0)
+            if timing is not None:
+                timing[1].record()
+                entry.eager_events = timing
         except Exception as e:
             if mode == "eager":
                 raise
@@ -511,11 +534,12 @@ def _weights_fingerprint(model_wrap):
 
 
 class _EngineEntry:
-    __slots__ = ("engine", "job", "runs", "graph_failed", "last_mode", "weights", "keep", "pinned")
+    __slots__ = ("engine", "job", "runs", "graph_failed", "last_mode", "weights", "keep", "pinned", "eager_events")
 
     def __init__(self):
         self.engine = self.job = None
         self.pinned = []
+        self.eager_events = None   # CUDA events around the previous job: how long this configuration takes
         self.runs = 0
         self.graph_failed = False
         self.last_mode = None
@@ -560,7 +584,7 @@ class _EngineCache:
 
 
 _ENGINES = _EngineCache()
-LAST_RUN = {"mode": None, "fused": False, "job": None, "events": None}   # how the most recent sample call was launched
+LAST_RUN = {"mode": None, "fused": False, "job": None, "events": None, "events_call": None}   # how the most recent sample call was launched
 
 
 _override_active = False

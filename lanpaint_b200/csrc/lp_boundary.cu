@@ -215,7 +215,7 @@ int launch_boundary_tma(const BoundaryArgs& p, cudaStream_t s) {
 
 template <typename H>
 int boundary_dispatch(const BoundaryArgs& p, bool v4, int dtype, cudaStream_t s) {
-  const bool tma = v4 && g_opt_tma != 0 && p.x && geometry_tma(p.g, p.mask) && p.g.total >= (uint32_t)g_opt_tma_min &&
+  const bool tma = v4 && g_opt_tma != 0 && g_opt_tma_boundary != 0 && p.x && geometry_tma(p.g, p.mask) && p.g.total >= (uint32_t)g_opt_tma_min &&
                    aligned16(p.a) && (!p.combine || aligned16(p.b)) && aligned16(p.y) && aligned16(p.x) &&
                    (!p.next_table || aligned16(p.noise)) && (!p.out || aligned16(p.out));
   if (tma) {

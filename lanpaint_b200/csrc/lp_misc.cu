@@ -19,6 +19,14 @@ int g_opt_tma_min = [] {
   return e ? atoi(e) : (1 << 18);
 }();
 
+// Measured (profiles/README.md, round 2): inside a job the LDG boundary kernel beats the TMA-staged one (its inputs
+// were just written by the network and sit in L2, and it skips the operands a vector's mask makes unnecessary):
+// 4.17 vs 4.30 ms per 128-request job.  The TMA variant stays available, off by default.
+int g_opt_tma_boundary = [] {
+  const char* e = getenv("LANPAINT_B200_TMA_BOUNDARY");
+  return e ? atoi(e) : 0;
+}();
+
 int current_device() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -221,6 +229,7 @@ extern "C" int lp_set_option(const char* name, int value) {
   if (eq("pdl")) { g_opt_pdl = value; return LP_OK; }
   if (eq("tma")) { g_opt_tma = value; return LP_OK; }
   if (eq("tma_min")) { g_opt_tma_min = value; return LP_OK; }
+  if (eq("tma_boundary")) { g_opt_tma_boundary = value; return LP_OK; }
   return LP_ERR_INVALID;
 }
 

@@ -234,7 +234,9 @@ class GraphedJob:
     sub-steps, epilogue) and the Euler updates between them -- on static buffers, launched in one of
     three ways that share ONE body (`_step`):
 
-      mode "job"    the whole job is ONE CUDA graph (captured once, replayed per batch of requests);
+      mode "job"    the whole job is ONE CUDA graph (captured once, replayed per batch of requests); with a callback
+                    every outer step writes its denoised latent to its own buffer and the callbacks run, in order,
+                    after the replay (for jobs so short that nobody can watch a progress bar move);
       mode "steps"  one CUDA graph per outer step, replayed in order with a host callback between them
                     (ComfyUI's progress / preview callback wants the denoised latent of every step);
       mode "eager"  plain launches (the first job of a configuration: nothing is wasted on warm-up).
@@ -303,6 +305,8 @@ class GraphedJob:
         self.first_replace_noop = bool(first_replace_noop) and fused_euler
         self._graphs = {}
         self._dims = None
+        self.timing, self.last_events = False, None
+        self.outs = None     # per-outer-step denoised latents (mode "job" with a callback: callbacks run after the replay)
         self.launches = 0
         self.model_calls = 0
         self.captures = 0
@@ -317,6 +321,9 @@ class GraphedJob:
         """The whole-job graph (None until the first mode="job" run)."""
         return self._graphs.get(("job", False))
 
+    def per_step_bytes(self) -> int:
+        return len(self.sched.steps) * self.x.numel() * 4
+
     # ---- the body ------------------------------------------------------------------------------
     def _init_state(self):
         sampling = self.engine.inner_model.inner_model.model_sampling
@@ -329,6 +336,8 @@ class GraphedJob:
         last = i + 1 == len(self.sched.steps)
         plan.used = self.draws_before[i]
         out = self.out if (want_out or not self.fused_euler) else None
+        if want_out == "each":      # every outer step keeps its own denoised latent
+            out = self.outs[i]
         eng._launch_sequence(self.x, self.y, self.noise, self.mask, self._dims, self.tables[i], self.t_model[i],
                              self.sigma[i], self.c, out, self.active[i], plan, False, self.model_options, self.seed,
                              None, self.rng_state.data_ptr(), euler_coef=coef if self.fused_euler else None,
@@ -420,19 +429,30 @@ class GraphedJob:
             raise ValueError("x_init must be given exactly when the job was built with external_init=True")
         if mode is None:
             mode = "steps" if callback is not None else "job"
+        if mode not in ("job", "steps", "eager"):
+            raise ValueError(f"unknown mode {mode!r}")
         with torch.cuda.device(self.device):
             before = (eng.launches, eng.model_calls)
             self.load_inputs(latent_image, noise, mask, x_init)
             plan = self._plan_cls(eng.rng, self.x, 1)
             self.rng_state.copy_(torch.from_numpy(plan.state_words().view(np.int64)))
+            if self.timing:   # device time of the sampler loop proper: inputs resident, first kernel -> last kernel
+                self.last_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                self.last_events[0].record()
             n_steps = len(self.sched.steps)
             want_out = callback is not None
-            if mode == "job" and not want_out:
-                graph, stats = self._graph_for(("job", False), lambda p: self._body(p, False), warm)
+            if mode == "job":
+                if want_out and self.outs is None:
+                    self.outs = [torch.empty_like(self.x) for _ in range(n_steps)]
+                each = "each" if want_out else False
+                graph, stats = self._graph_for(("job", each), lambda p: self._body(p, each), warm)
                 graph.replay()
                 eng.launches += stats[0]
                 eng.model_calls += stats[1]
-            elif mode in ("steps", "job"):
+                if callback is not None:
+                    for i in range(n_steps):
+                        callback(i, self.outs[i], self.x, n_steps)
+            elif mode == "steps":
                 if not self.external_init:
                     self._init_state()
                 for i in range(n_steps):
@@ -452,6 +472,8 @@ class GraphedJob:
                         callback(i, self.out, self.x, n_steps)
             else:
                 raise ValueError(f"unknown mode {mode!r}")
+            if self.timing:
+                self.last_events[1].record()
             plan.consume(self.draws)
             plan.finish()
             eng.substeps_done += self.sched.substeps

@@ -18,7 +18,7 @@ from lanpaint_b200.runner import SynthCondNet  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--requests", type=int, default=128)
 ap.add_argument("--rng", default="torch")
-ap.add_argument("--calls", type=int, default=6)
+ap.add_argument("--calls", type=int, default=8)
 ap.add_argument("--sampler", default="euler")
 ap.add_argument("--no-graph", action="store_true")
 ap.add_argument("--no-fused", action="store_true")

@@ -29,6 +29,8 @@ ap.add_argument("--requests", type=int, nargs="+", default=[1, 8, 128])
 ap.add_argument("--rng", default="torch")
 ap.add_argument("--jobs", type=int, default=5)
 ap.add_argument("--no-callback", action="store_true", help="call the guider without a progress callback: whole-job graph")
+ap.add_argument("--per-step", action="store_true",
+                help="one graph per outer step with the callback between them even for short jobs (deferred_callbacks=False)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 
@@ -66,14 +68,14 @@ def union_length(iv):
 
 
 print(f"# torch.profiler (CUPTI) timeline of the sampler loop, node API, rng={args.rng}, "
-      f"{'whole-job graph (no callback)' if args.no_callback else 'one graph per outer step (ComfyUI progress callback)'}")
+      f"{'whole-job graph (no callback)' if args.no_callback else ('one graph per outer step, ComfyUI progress callback between them' if args.per_step else 'default: ComfyUI progress callback; short jobs run as one graph, callbacks delivered after it')}")
 print("# requests  job  kernels  span_us  busy_us  gap_%   largest_idle_us")
 for R in args.requests:
     g = torch.Generator().manual_seed(0)
     y = torch.randn(R, 4, 128, 128, generator=g)
     noise_mask = (torch.rand(R, 1, 128, 128, generator=g) < 0.5).float()
     patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(SynthCondNet()), dev)
-    patcher.model_options["lanpaint_b200"] = {"rng": args.rng}
+    patcher.model_options["lanpaint_b200"] = {"rng": args.rng, "deferred_callbacks": not args.per_step}
     node = N.LanPaint_KSampler()
 
     def call(seed):
@@ -88,7 +90,7 @@ for R in args.requests:
         with N.override_sample_function():
             return guider.sample(minicomfy.prepare_noise(y, seed), y, minicomfy.ksampler("euler"), sig,
                                  denoise_mask=noise_mask, seed=seed)
-    for k in range(3):      # eager, capture, replay
+    for k in range(4):      # eager, capture, replay
         call(k)
     torch.cuda.synchronize()
     gaps = []
@@ -97,7 +99,7 @@ for R in args.requests:
             call(100 + j)
             torch.cuda.synchronize()
         rec = [(n, s, e) for (n, s, e) in kernel_records(prof)]
-        lp = [(s, e) for (n, s, e) in rec if "lp::" in n]
+        lp = [(s, e) for (n, s, e) in rec if "lp::" in n and "pack_mask" not in n]   # the sampler loop proper
         if not lp:
             print(f"{R:9d} {j:4d}  no lp:: kernel records (profiler unavailable?)")
             continue

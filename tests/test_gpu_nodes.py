@@ -236,18 +236,24 @@ def test_node_default_is_graph_replay_and_matches_oracle(cuda_device):
     g = torch.Generator().manual_seed(6)
     y = torch.randn(2, 4, 32, 32, generator=g)
     noise_mask = (torch.rand(2, 1, 32, 32, generator=g) < 0.5).float()
-    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
-    outs, modes = [], []
-    calls0 = minicomfy.PROGRESS["calls"]
-    for _ in range(4):
-        o, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher)
-        outs.append(o)
-        modes.append(N.LAST_RUN["mode"])
-        eng = N.LAST_ENGINE["engine"]
-        assert eng.model_calls == 73 and eng.substeps_done == 53 and eng.rng == "torch"
-    assert modes == ["eager", "steps", "steps", "steps"], modes
-    assert minicomfy.PROGRESS["calls"] - calls0 == 4 * 20 and minicomfy.PROGRESS["last"] == (20, 20)
-    assert N.LAST_RUN["job"].captures == 20
+    outs = []
+    for deferred, want_modes, want_captures in ((False, ["eager", "steps", "steps", "steps"], 20),
+                                                (True, ["eager", "job", "job", "job"], 1)):
+        # a job this short (a pointwise network) runs as ONE graph with the callbacks delivered right after it;
+        # {"deferred_callbacks": False} -- or a job longer than 20 ms, i.e. any real network -- keeps one graph per
+        # outer step with the callback between them
+        patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+        modes = []
+        calls0 = minicomfy.PROGRESS["calls"]
+        for _ in range(4):
+            o, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, opts={"deferred_callbacks": deferred})
+            outs.append(o)
+            modes.append(N.LAST_RUN["mode"])
+            eng = N.LAST_ENGINE["engine"]
+            assert eng.model_calls == 73 and eng.substeps_done == 53 and eng.rng == "torch"
+        assert modes == want_modes, modes
+        assert minicomfy.PROGRESS["calls"] - calls0 == 4 * 20 and minicomfy.PROGRESS["last"] == (20, 20)
+        assert N.LAST_RUN["job"].captures == want_captures
     for o in outs[1:]:
         assert torch.equal(o, outs[0])
     noise = minicomfy.prepare_noise(y, 11)        # re-seeds every generator exactly like the node call did
@@ -271,16 +277,16 @@ def test_node_cache_is_keyed_on_what_a_graph_bakes_in(cuda_device):
     y = torch.randn(1, 4, 32, 32, generator=g)
     noise_mask = (torch.rand(1, 1, 32, 32, generator=g) < 0.5).float()
     patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
-    for _ in range(3):   # cfg 5 is now graph-replayed
+    for _ in range(5):   # cfg 5 is now graph-replayed (eager -> [per-step graphs ->] whole-job graph once it proved short)
         a5, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, steps=8, n=3)
-    assert N.LAST_RUN["mode"] == "steps"
+    assert N.LAST_RUN["mode"] == "job"
     a7, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, steps=8, n=3, cfg=7.0)
     assert N.LAST_RUN["mode"] == "eager"
     ref7, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False}, steps=8, n=3, cfg=7.0)
     assert torch.equal(a7, ref7) and not torch.equal(a7, a5)
     # another seed replays the same graphs with a fresh noise image and a fresh randn stream
     b5, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, steps=8, n=3, seed=12)
-    assert N.LAST_RUN["mode"] == "steps"
+    assert N.LAST_RUN["mode"] == "job"
     refb, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False}, steps=8, n=3, seed=12)
     assert torch.equal(b5, refb) and not torch.equal(b5, a5)
     # a float conditioning of equal value is the same prompt for minicomfy; a different value is not

@@ -820,7 +820,7 @@ def test_boundary_tma_variant_is_bit_identical(combine, with_next, with_out, cud
     coef, cfg = -0.37, 3.5
 
     def run(tma):
-        assert lib.lp_set_option(b"tma", tma) == 0
+        assert lib.lp_set_option(b"tma", tma) == 0 and lib.lp_set_option(b"tma_boundary", tma) == 0
         x, out = x0.clone(), torch.full(shape, float("nan"), device=dev)
         h = _native.Heads(a.data_ptr(), b.data_ptr() if combine else None, _native.DTYPE_F32, 1 if combine else 0, cfg, cfg)
         rc = lib.lp_boundary(C.byref(h), P(y.data_ptr()), P(nz.data_ptr()) if with_next else None, P(m8.data_ptr()),
@@ -834,6 +834,7 @@ def test_boundary_tma_variant_is_bit_identical(combine, with_next, with_out, cud
         x0_, o0 = run(0)
     finally:
         lib.lp_set_option(b"tma", 1)
+        lib.lp_set_option(b"tma_boundary", 0)   # the default (the LDG kernel measured faster inside a job)
     assert torch.equal(x1, x0_)
     known = m8.bool().expand(shape)
     d = b + (a - b) * cfg if combine else a
