@@ -125,6 +125,30 @@ def test_reshape_mask_matches_reference_outputs(nodes_mod):
         assert torch.equal(got.contiguous(), torch.from_numpy(z["out_" + key])), key
 
 
+def test_prepare_mask_keeps_the_reference_values_while_travelling_compact(nodes_mod):
+    """prepare_mask == reshape_mask(...).to(device) in values and shape (every golden case of the reference's own
+    function); single-channel masks come back as a stride-0 expansion (1/C of the bytes cross PCIe) and a mask
+    that needs no resampling may arrive as uint8 / bool."""
+    import numpy as np
+    import torch
+    src = open(os.path.join(GOLDEN_DIR, "make_golden.py")).read()
+    ns = {}
+    exec(src[src.index("RESHAPE_CASES = {"):src.index("def dump_node_api")], ns)
+    z = np.load(os.path.join(GOLDEN_DIR, "aux_reshape_mask_cases.npz"))
+    for key, (mshape, oshape, video) in ns["RESHAPE_CASES"].items():
+        got = nodes_mod.prepare_mask(torch.from_numpy(z["in_" + key]), oshape, "cpu", video_inpainting=video)
+        assert tuple(got.shape) == tuple(oshape), key
+        assert torch.equal(got.contiguous(), torch.from_numpy(z["out_" + key])), key
+    m = (torch.rand(3, 1, 16, 16) > 0.5)
+    want = nodes_mod.reshape_mask(m.float(), (3, 4, 16, 16))
+    for src_mask in (m, m.to(torch.uint8), m.float(), m[:, 0].float()):
+        got = nodes_mod.prepare_mask(src_mask, (3, 4, 16, 16), "cpu")
+        assert got.dtype == torch.float32 and got.stride(1) == 0 and torch.equal(got, want)
+    full = (torch.rand(2, 4, 8, 8) > 0.5).float()          # a mask that differs per channel stays materialised
+    got = nodes_mod.prepare_mask(full, (2, 4, 8, 8), "cpu")
+    assert torch.equal(got, full) and got.stride(1) != 0
+
+
 # ---- MiniMax-H3 detection (reference tests/test_av_schedule.py:75-105) -----------------------------------
 class _FakeDiffusion:
     sigma_shift_video = 12.0
