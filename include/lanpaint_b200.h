@@ -141,8 +141,9 @@ int lp_last_cuda_error(void); /* cudaError_t of the last failed launch on this t
  *   "pdl" 1|0      programmatic dependent launch on every kernel (default 1)
  *   "tma" 1|0      use the TMA-staged persistent variants (cp.async.bulk + mbarrier ring) of the fused sub-step
  *                  (philox and torch streams) and of the step-boundary kernel when eligible: spatial a multiple
- *                  of 16, no side outputs, no row split (default 1; 2.. select alternative tile geometries of
- *                  the philox kernel for measurement)
+ *                  of 16, no side outputs, no row split (default 1; 2..5 select alternative tile geometries of
+ *                  the philox kernel and 8 the two-subsequences-per-thread geometry of the torch kernel, for
+ *                  measurement)
  *   "tma_min"      smallest launch, in elements, that takes a TMA-staged variant (default 2^18)
  *   "tma_boundary" 1|0  lp_boundary: TMA-staged kernel when eligible | always the LDG kernel (default 0: measured
  *                  faster inside a job, where the network's output is still in L2) */

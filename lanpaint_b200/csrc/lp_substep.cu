@@ -606,42 +606,23 @@ __device__ __forceinline__ void torch_tma_body2(const SubstepArgs& a, const Torc
   }
 }
 
-// <448 subsequences per group, 224 consumer threads + producer warp = 256 threads, up to 4 CTAs per SM, 64 registers>
+// <448 subsequences per group, 224 consumer threads + producer warp = 256 threads, up to 4 CTAs per SM, 64 registers>.
+// Bit-identical to the default geometry and measured SLOWER (48.7 vs 43.6 us per launch at R=128; with 3 CTAs per SM
+// and 80 registers 50.3 us): kept selectable (lp_set_option("tma", 8)) as the reproducible form of that result.
 template <typename H, bool kFirst, bool kNext>
 __global__ void __launch_bounds__(448 / 2 + 32, 4) substep_torch_tma_kernel_p2(const SubstepArgs a, const TorchTmaGeom tg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[4], empty[4];
   torch_tma_body2<H, kFirst, kNext, 448>(a, tg, smem_raw, full, empty);
 }
-// <448, 3 CTAs per SM, 80 registers>
-template <typename H, bool kFirst, bool kNext>
-__global__ void __launch_bounds__(448 / 2 + 32, 3) substep_torch_tma_kernel_p2r80(const SubstepArgs a, const TorchTmaGeom tg) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full[4], empty[4];
-  torch_tma_body2<H, kFirst, kNext, 448>(a, tg, smem_raw, full, empty);
-}
-
-// launch geometries: <kG, CTAs per SM>.  The default (1024, 2) keeps two independent CTAs per SM; (2048, 1) trades
-// that for a higher register ceiling per thread (more Box-Muller chains in flight); _r112 is (1024, 2) with the
-// register ceiling spelled out instead of derived from the launch bounds.
+// The default geometry: <1024 subsequences per group, 256 consumer threads + producer warp, 2 CTAs per SM, 96
+// registers>.  Measured and dropped: a 112-register ceiling (one CTA per SM, 70 us) and 2048-subsequence groups with 17
+// warps (does not launch).
 template <typename H, bool kFirst, bool kNext>
 __global__ void __launch_bounds__(1024 / 4 + 32, 2) substep_torch_tma_kernel(const SubstepArgs a, const TorchTmaGeom tg) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full[4], empty[4];
   torch_tma_body<H, kFirst, kNext, 1024>(a, tg, smem_raw, full, empty);
-}
-template <typename H, bool kFirst, bool kNext>
-__global__ void __maxnreg__(112)
-    substep_torch_tma_kernel_r112(const SubstepArgs a, const TorchTmaGeom tg) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full[4], empty[4];
-  torch_tma_body<H, kFirst, kNext, 1024>(a, tg, smem_raw, full, empty);
-}
-template <typename H, bool kFirst, bool kNext>
-__global__ void __maxnreg__(120) substep_torch_tma_kernel_g2048(const SubstepArgs a, const TorchTmaGeom tg) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full[4], empty[4];
-  torch_tma_body<H, kFirst, kNext, 2048>(a, tg, smem_raw, full, empty);
 }
 
 // ---- TORCH, 128-bit LDG path ----------------------------------------------------------------------
@@ -814,45 +795,28 @@ int launch_substep_vec(const SubstepArgs& a, bool first, bool next, bool merge, 
 template <typename H, bool kFirst, bool kNext>
 int launch_torch_tma(const SubstepArgs& a, uint32_t calls, cudaStream_t s) {
   const int dev = current_device();
-  const int variant = (sizeof(H) == 4 && !kFirst && kNext) ? g_opt_tma : 1;   // alternatives: steady fp32 kernel only
-  const int kG = variant == 7 ? 2048 : 1024;
-  const size_t smem = (variant == 7 ? sizeof(TorchSlot<H, 2048>) : sizeof(TorchSlot<H, 1024>)) * 4;
-  TorchTmaGeom tg;
-  tg.groups_per_call = a.torch_T / kG;
-  tg.n_groups = calls * tg.groups_per_call;
-  unsigned grid = (unsigned)device_info(dev).sms * (variant == 7 ? 1u : 2u);
-  if (grid > tg.n_groups) grid = tg.n_groups;
-  if (variant == 8 || variant == 9) {   // two subsequences per thread, groups of 448 (need not divide T)
-    const size_t smem2 = sizeof(TorchSlot<H, 448>) * 4;
-    TorchTmaGeom t2;
-    t2.groups_per_call = (a.torch_T + 447u) / 448u;
-    t2.n_groups = calls * t2.groups_per_call;
-    unsigned g2 = (unsigned)device_info(dev).sms * (variant == 8 ? 4u : 3u);
-    if (g2 > t2.n_groups) g2 = t2.n_groups;
-    if (variant == 8) {
-      static bool configured[kMaxDevices] = {};
-      ensure_dynamic_smem(substep_torch_tma_kernel_p2<H, kFirst, kNext>, smem2, dev, configured);
-      launch_kernel_ex(substep_torch_tma_kernel_p2<H, kFirst, kNext>, dim3(g2), dim3(448 / 2 + 32), smem2, s, a, t2);
-    } else {
-      static bool configured[kMaxDevices] = {};
-      ensure_dynamic_smem(substep_torch_tma_kernel_p2r80<H, kFirst, kNext>, smem2, dev, configured);
-      launch_kernel_ex(substep_torch_tma_kernel_p2r80<H, kFirst, kNext>, dim3(g2), dim3(448 / 2 + 32), smem2, s, a, t2);
-    }
+  const int variant = (sizeof(H) == 4 && !kFirst && kNext) ? g_opt_tma : 1;   // the alternative: steady fp32 kernel only
+  if (variant == 8) {   // two subsequences per thread, groups of 448 (need not divide T)
+    const size_t smem = sizeof(TorchSlot<H, 448>) * 4;
+    TorchTmaGeom tg;
+    tg.groups_per_call = (a.torch_T + 447u) / 448u;
+    tg.n_groups = calls * tg.groups_per_call;
+    unsigned grid = (unsigned)device_info(dev).sms * 4u;
+    if (grid > tg.n_groups) grid = tg.n_groups;
+    static bool configured[kMaxDevices] = {};
+    ensure_dynamic_smem(substep_torch_tma_kernel_p2<H, kFirst, kNext>, smem, dev, configured);
+    launch_kernel_ex(substep_torch_tma_kernel_p2<H, kFirst, kNext>, dim3(grid), dim3(448 / 2 + 32), smem, s, a, tg);
     return check_launch();
   }
-  if (variant == 7) {
-    static bool configured[kMaxDevices] = {};
-    ensure_dynamic_smem(substep_torch_tma_kernel_g2048<H, kFirst, kNext>, smem, dev, configured);
-    launch_kernel_ex(substep_torch_tma_kernel_g2048<H, kFirst, kNext>, dim3(grid), dim3(2048 / 4 + 32), smem, s, a, tg);
-  } else if (variant == 6) {
-    static bool configured[kMaxDevices] = {};
-    ensure_dynamic_smem(substep_torch_tma_kernel_r112<H, kFirst, kNext>, smem, dev, configured);
-    launch_kernel_ex(substep_torch_tma_kernel_r112<H, kFirst, kNext>, dim3(grid), dim3(1024 / 4 + 32), smem, s, a, tg);
-  } else {
-    static bool configured[kMaxDevices] = {};
-    ensure_dynamic_smem(substep_torch_tma_kernel<H, kFirst, kNext>, smem, dev, configured);
-    launch_kernel_ex(substep_torch_tma_kernel<H, kFirst, kNext>, dim3(grid), dim3(1024 / 4 + 32), smem, s, a, tg);
-  }
+  const size_t smem = sizeof(TorchSlot<H, 1024>) * 4;
+  TorchTmaGeom tg;
+  tg.groups_per_call = a.torch_T / 1024;
+  tg.n_groups = calls * tg.groups_per_call;
+  unsigned grid = (unsigned)device_info(dev).sms * 2u;
+  if (grid > tg.n_groups) grid = tg.n_groups;
+  static bool configured[kMaxDevices] = {};
+  ensure_dynamic_smem(substep_torch_tma_kernel<H, kFirst, kNext>, smem, dev, configured);
+  launch_kernel_ex(substep_torch_tma_kernel<H, kFirst, kNext>, dim3(grid), dim3(1024 / 4 + 32), smem, s, a, tg);
   return check_launch();
 }
 
@@ -864,7 +828,7 @@ int substep_dispatch(SubstepArgs& a, const lp_rng* rng, bool f, bool n, bool mer
     a.torch_T = (uint32_t)(grid * 256);
     const unsigned gb = (unsigned)grid;
     const uint64_t calls = ((uint64_t)a.g.total + 4ull * a.torch_T - 1) / (4ull * a.torch_T);
-    if (v4 && tma_eligible(a) && a.torch_T % 2048 == 0 && a.g.spatial.d >= 64 && calls <= 0xffffffffull / 4) {
+    if (v4 && tma_eligible(a) && a.torch_T % 1024 == 0 && a.g.spatial.d >= 64 && calls <= 0xffffffffull / 4) {
       if (f && n) return launch_torch_tma<H, true, true>(a, (uint32_t)calls, s);
       if (f) return launch_torch_tma<H, true, false>(a, (uint32_t)calls, s);
       if (n) return launch_torch_tma<H, false, true>(a, (uint32_t)calls, s);

@@ -744,16 +744,17 @@ def test_torch_stream_tma_variant_is_bit_identical(cuda_device):
             x, y, noise, m = synth_inputs(shape, seed=33, device=dev)
             sig = torch.full((shape[0],), 1.3)
             times = tuple(O.times_from_sigma(sig, False))
-            for tma in (0, 1):
+            for tma in (0, 1, 8):     # LDG kernels, the default TMA geometry, two subsequences per thread
                 assert lib.lp_set_option(b"tma", tma) == 0
                 torch.manual_seed(23)
                 eng = _engine(SynthDenoiser(VESampling()), dict(n_steps=4), rng="torch", batched_replace="per_sample")
                 xx = x.clone()
                 out = eng(xx, y, noise, sig, m, times, None, 0, n_steps=4)
                 res[(shape, tma)] = (out, xx, torch.cuda.default_generators[dev.index or 0].get_offset())
-            assert torch.equal(res[(shape, 0)][0], res[(shape, 1)][0]), shape
-            assert torch.equal(res[(shape, 0)][1], res[(shape, 1)][1]), shape
-            assert res[(shape, 0)][2] == res[(shape, 1)][2]
+            for tma in (1, 8):
+                assert torch.equal(res[(shape, 0)][0], res[(shape, tma)][0]), (shape, tma)
+                assert torch.equal(res[(shape, 0)][1], res[(shape, tma)][1]), (shape, tma)
+                assert res[(shape, 0)][2] == res[(shape, tma)][2]
     finally:
         lib.lp_set_option(b"tma", 1)
 
