@@ -490,7 +490,7 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
         try:
             out = job.run(latent_image, model_k.noise, pm, x_init=x_init, callback=callback, mode=mode,
                           warm=after <= 0)
-            if timing is not None:
+            if timing is not None and job.captures == captures:   # a run that captured graphs also timed the capture
                 timing[1].record()
                 entry.eager_events = timing
         except Exception as e:

@@ -255,6 +255,7 @@ class LanPaint:
         self._noise_zero_cache = _IdentityCache()
         self._av_cache = _IdentityCache()
         self._av_mask_cache = _IdentityCache()
+        self._replace_probe_cache = {}
         self._ws = {}
         self.stats_reduce = None  # frame_shard.py: sums the early stopper's two statistics over the shards of a latent
         self.kernel_timer = None  # set to a list to collect (flags, start_event, stop_event) per substep launch
@@ -316,11 +317,13 @@ class LanPaint:
         if mode != "probe":
             return None
         rn, ry = [], []
-        seen = {}
+        seen = self._replace_probe_cache.setdefault(id(sampling), {})   # one probe per distinct sigma per run
+        if len(seen) > 4096:
+            seen.clear()
         for s in (sigma_host if not scalar_sigma else sigma_host[:1]):
             s = float(s)
             form = seen.get(s)
-            if form is None:  # one probe per distinct sigma, not per sample
+            if form is None:
                 form = seen[s] = _probe_noise_scaling(sampling, s) or False
             if form is False:
                 return None

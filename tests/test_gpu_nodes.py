@@ -413,3 +413,56 @@ def test_av_flat_pack_through_the_node_layer(cuda_device, monkeypatch):
         x = x + (x - den) / host[i] * (host[i + 1] - host[i])
     want = Guider().model_sampling.inverse_noise_scaling(sig[-1].to(dev), x)
     assert max_rel(got, want) <= 1e-5
+
+
+def test_a_real_torch_module_under_the_node_graphs(cuda_device):
+    """The network is an nn.Module with cuDNN convolutions (what ComfyUI's diffusion_model is): it is captured inside
+    the node path's graphs; in-place weight updates are picked up by replays (graphs read weights by address); moving
+    the weights to new storage (ComfyUI off-loading / re-loading the model) drops the cached graphs."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    N._ENGINES.clear()
+    dev = cuda_device
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3, padding=1), torch.nn.SiLU(),
+                                            torch.nn.Conv2d(8, 4, 3, padding=1))
+
+        def forward(self, x, sigma, cond):
+            return 0.6 * x + 0.1 * self.body(x) + cond
+    torch.manual_seed(0)
+    net = Net().to(dev)
+    g = torch.Generator().manual_seed(4)
+    y = torch.randn(2, 4, 32, 32, generator=g)
+    noise_mask = (torch.rand(2, 1, 32, 32, generator=g) < 0.5).float()
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(net), dev)
+
+    def run(p=patcher, opts=None):
+        with torch.no_grad():
+            out, _ = _ksampler_run(N, dev, y, noise_mask, patcher=p, opts=opts, steps=8, n=3)
+        return out, N.LAST_RUN["mode"]
+
+    outs, modes = zip(*[run() for _ in range(5)])
+    assert modes[0] == "eager" and modes[-1] in ("steps", "job")
+    for o in outs[1:]:
+        assert max_rel(o, outs[0]) <= 1e-5        # cuDNN may pick another algorithm under capture: not bitwise
+    # in-place weight update: same storage, the replayed graph must see the new values
+    with torch.no_grad():
+        for prm in net.parameters():
+            prm.mul_(1.25)
+    replayed, mode = run()
+    assert mode == modes[-1]
+    fresh, _ = run(minicomfy.ModelPatcher(minicomfy.BaseModel(net), dev), {"cuda_graph": False})
+    assert max_rel(replayed, fresh) <= 1e-5 and max_rel(replayed, outs[0]) > 1e-3
+    # new storage for the weights: graphs captured against the old addresses must not be replayed
+    before = tuple(prm.data_ptr() for prm in net.parameters())
+    net.to("cpu")
+    hold = [torch.empty(4096, device=dev) for _ in range(64)]     # occupy the freed blocks: force new addresses
+    net.to(dev)
+    moved, mode = run()
+    del hold
+    if tuple(prm.data_ptr() for prm in net.parameters()) != before:
+        assert mode == "eager"
+    assert max_rel(moved, fresh) <= 1e-5
