@@ -255,7 +255,7 @@ class LanPaint:
         self._noise_zero_cache = _IdentityCache()
         self._av_cache = _IdentityCache()
         self._av_mask_cache = _IdentityCache()
-        self._replace_probe_cache = {}
+        self._replace_probe_cache = {"sampling": None, "seen": {}}
         self._ws = {}
         self.stats_reduce = None  # frame_shard.py: sums the early stopper's two statistics over the shards of a latent
         self.kernel_timer = None  # set to a list to collect (flags, start_event, stop_event) per substep launch
@@ -317,9 +317,10 @@ class LanPaint:
         if mode != "probe":
             return None
         rn, ry = [], []
-        seen = self._replace_probe_cache.setdefault(id(sampling), {})   # one probe per distinct sigma per run
-        if len(seen) > 4096:
-            seen.clear()
+        cache = self._replace_probe_cache            # one probe per distinct sigma of one model_sampling object
+        if cache.get("sampling") is not sampling or len(cache["seen"]) > 4096:
+            cache["sampling"], cache["seen"] = sampling, {}
+        seen = cache["seen"]
         for s in (sigma_host if not scalar_sigma else sigma_host[:1]):
             s = float(s)
             form = seen.get(s)
