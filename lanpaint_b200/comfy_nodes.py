@@ -268,6 +268,9 @@ class KSamplerX0Inpaint:
         self.audio_indicator = None
         self.audio_shifts = None
         self._mask_cache = _IdentityCache()
+        self.trace = None          # list: record (sigma, times, n_eff) of every call (runner.SamplerGraphJob)
+        self.planned_call = None   # set while a whole sampler loop is being captured: serves the recorded calls
+        self.rng_delta = 0         # CUDA generator offset consumed by the engine calls (vs. by the sampler itself)
 
     def _latent_mask(self, denoise_mask, like):
         """1 - (denoise_mask > 0.5), packed once per distinct mask tensor (nodes.py:281-283)."""
@@ -289,6 +292,8 @@ class KSamplerX0Inpaint:
         mtype = self.inner_model.inner_model.model_type
         is_flux = mtype == ModelType.FLUX
         is_flow = mtype in FLOW_MODEL_TYPES
+        if denoise_mask is not None and self.planned_call is not None:
+            return self.planned_call(x, model_options, seed)     # capture of the whole sampler loop: nothing is read back
         if denoise_mask is None:
             out, _ = self.PaintMethod.unpack_model_output(
                 self.inner_model(x, sigma, model_options=model_options, seed=seed))
@@ -316,9 +321,14 @@ class KSamplerX0Inpaint:
                 audio = dict(current_times_audio=(flow_a / (1 - flow_a), abt_a, flow_a),
                              audio_indicator=self.audio_indicator,
                              audio_correction=(1.0 - self.audio_indicator) + c * self.audio_indicator)
+            if self.trace is not None:
+                self.trace.append((sigma_host.clone(), tuple(t.clone() for t in times), n_eff))
+            gen = torch.cuda.default_generators[x.device.index if x.device.index is not None else torch.cuda.current_device()]
+            before = gen.get_offset()
             out = self.PaintMethod(x, self.latent_image, self.noise, sigma_host,
                                    self._latent_mask(denoise_mask, x), times, model_options, seed, n_steps=n_eff,
                                    **audio)
+            self.rng_delta += gen.get_offset() - before
         step = model_options.get("i", kwargs.get("i", 0))
         if step % 2 == 0:  # preview every other step (nodes.py:304-313)
             callback = model_options.get("callback", None)
@@ -406,12 +416,34 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
             samples = KSAMPLER._fused_euler(self, model_k, entry, engine, x_init, latent_image, denoise_mask, model_options,
                                         extra_args.get("seed"), is_flux or is_flow, early_stop, callback, total_steps,
                                         use_graph, opts)
+        sg_ok = False
+        if samples is None and use_graph and entry is not None and opts.get("sampler_graph", True):
+            sg_ok = KSAMPLER._sampler_graph_ok(self, model_k, denoise_mask, model_options, engine, entry)
+            if sg_ok and isinstance(entry.trace, list):
+                samples = KSAMPLER._sampler_graph(self, model_k, entry, engine, x_init, latent_image, denoise_mask,
+                                                  model_options, extra_args, callback, opts)
         if samples is None:
             k_callback = None
             if callback is not None:
                 k_callback = lambda d: callback(d["i"], d["denoised"], d["x"], total_steps)  # noqa: E731
+            recording = sg_ok and entry.trace is None
+            if recording:       # first job of this configuration: plain launches, and remember what the sampler asked for
+                model_k.trace = []
+                engine.cuda_graph = False
+                gen = torch.cuda.default_generators[x_init.device.index if x_init.device.index is not None
+                                                    else torch.cuda.current_device()]
+                off0 = gen.get_offset()
+                t_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                t_ev[0].record()
             samples = self.sampler_function(model_k, x_init, sigmas, extra_args=extra_args, callback=k_callback,
                                             disable=disable_pbar, **self.extra_options)
+            if recording:
+                t_ev[1].record()
+                engine.cuda_graph = use_graph
+                own_draws = (gen.get_offset() - off0) != model_k.rng_delta     # the sampler drew noise itself
+                entry.trace = False if (own_draws or not model_k.trace) else model_k.trace
+                entry.eager_events = t_ev
+                model_k.trace = None
         self.last_engine = engine
         if timing is not None:
             timing[1].record()
@@ -474,13 +506,13 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
         else:
             # ComfyUI always passes a callback (progress bar / preview / interrupt check).  One graph per outer step
             # keeps it live -- right for a real network, where a step takes long enough to watch.  When the eager
-            # job of this configuration took only a few milliseconds nobody can watch anything: the whole job runs
+            # job of this configuration took only a few (< 50) milliseconds nobody can watch anything: the whole job runs
             # as ONE graph, each outer step keeps its denoised latent, and the callbacks run in order right after.
             dev_ms = None      # device time of this configuration's previous job (the very first one of a process
             if entry.eager_events is not None:   # also pays CUDA's lazy module loading and is re-measured)
                 dev_ms = entry.eager_events[0].elapsed_time(entry.eager_events[1])
             deferred = (opts.get("deferred_callbacks", True) and dev_ms is not None
-                        and dev_ms <= float(opts.get("deferred_max_ms", 20.0))
+                        and dev_ms <= float(opts.get("deferred_max_ms", 50.0))
                         and job.per_step_bytes() <= int(opts.get("deferred_max_bytes", 1 << 30)))
             mode = "job" if deferred else "steps"
         timing = None
@@ -514,6 +546,57 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
         return out if out.dtype == x_init.dtype else out.to(x_init.dtype)
 
 
+    # ---- any other deterministic sampler: the whole k-diffusion loop as one graph ------------------------------
+    def _sampler_graph_ok(self, model_k, denoise_mask, model_options, engine, entry) -> bool:
+        if entry.trace is False or entry.graph_failed:
+            return False
+        if denoise_mask is None or model_k.audio_indicator is not None:
+            return False
+        if "denoise_mask_function" in model_options or model_options.get("callback") is not None:
+            return False
+        if float(engine.early_stop_threshold or 0.0) > 0.0 or isinstance(model_options.get("lanpaint_semantic_stop"), dict):
+            return False
+        if engine.rng not in ("torch", "philox") or engine._noise_is_zero(model_k.noise):
+            return False
+        return True
+
+    def _sampler_graph(self, model_k, entry, engine, x_init, latent_image, denoise_mask, model_options, extra_args,
+                       callback, opts):
+        from .engine import _repair_generator_after_failed_capture
+        from .runner import SamplerGraphJob
+        job = entry.sampler_job
+        if job is None:
+            if callback is not None:     # callbacks can only be delivered after the replay: short jobs only
+                dev_ms = entry.eager_events[0].elapsed_time(entry.eager_events[1]) if entry.eager_events else None
+                nbytes = len(entry.trace) * x_init.numel() * 4
+                if not (opts.get("deferred_callbacks", True) and dev_ms is not None
+                        and dev_ms <= float(opts.get("deferred_max_ms", 50.0))
+                        and nbytes <= int(opts.get("deferred_max_bytes", 1 << 30))):
+                    entry.trace = False
+                    return None
+            job = entry.sampler_job = SamplerGraphJob(engine, self.sampler_function, self.extra_options,
+                                                      torch.tensor(model_k.sigmas_host), entry.trace,
+                                                      tuple(x_init.shape), x_init.device)
+        job.timing = bool(opts.get("timing"))
+        pm = model_k._latent_mask(denoise_mask, x_init)
+        captures = job.captures
+        try:
+            out = job.run(model_k, extra_args, latent_image, model_k.noise, pm, x_init, callback=callback)
+        except Exception as e:
+            import warnings
+            warnings.warn(f"lanpaint_b200: capturing the sampler loop failed ({type(e).__name__}: {e}); "
+                          "using one graph per wrapper call instead")
+            _repair_generator_after_failed_capture(x_init.device)
+            entry.trace, entry.sampler_job = False, None
+            engine.reset_counters()
+            return None
+        if job.captures != captures:
+            entry.pinned.append((model_k.inner_model, model_options))
+        entry.runs += 1
+        LAST_RUN.update(mode="sampler-graph", fused=False, job=job)
+        return out if out.dtype == x_init.dtype else out.to(x_init.dtype)
+
+
 # =============================================================================================
 # engines (and their CUDA graphs) kept across sample() calls
 # =============================================================================================
@@ -534,10 +617,13 @@ def _weights_fingerprint(model_wrap):
 
 
 class _EngineEntry:
-    __slots__ = ("engine", "job", "runs", "graph_failed", "last_mode", "weights", "keep", "pinned", "eager_events")
+    __slots__ = ("engine", "job", "runs", "graph_failed", "last_mode", "weights", "keep", "pinned", "eager_events",
+                 "trace", "sampler_job")
 
     def __init__(self):
         self.engine = self.job = None
+        self.trace = None           # None: not recorded yet; list: the wrapper calls of one job; False: not capturable
+        self.sampler_job = None
         self.pinned = []
         self.eager_events = None   # CUDA events around the previous job: how long this configuration takes
         self.runs = 0

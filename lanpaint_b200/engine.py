@@ -453,6 +453,42 @@ class LanPaint:
             input_x.copy_(xm)
         return out if out.dtype == input_x.dtype else out.to(input_x.dtype)
 
+    # ---- planned calls: everything host-side done ahead, the call itself is capture-safe -------------------
+    def plan_item(self, B: int, sigma_host: torch.Tensor, times, n_steps: int, device, sigma_shape=None):
+        """Everything `LanPaint()` derives on the host from (sigma, current_times) for ONE wrapper call, as device
+        constants: coefficient table, model timestep, sigma.  Used by runner.SamplerGraphJob, which records the
+        sigma sequence of a sampler's first (eager) job and then captures the whole sampler loop: the captured
+        calls must not read anything back.  Returns None when noise_scaling is not a linear form."""
+        flow = bool(self.IS_FLUX or self.IS_FLOW)
+        VE_Sigma, abt, Flow_t = times
+
+        def flat(t):
+            t = t.reshape(-1).to(device="cpu", dtype=torch.float32)
+            return t if t.numel() == B else t.expand(B)
+        host = torch.stack([flat(t) for t in (sigma_host, VE_Sigma, abt, Flow_t if flow else VE_Sigma)]).numpy()
+        sigma_h, ve_h, abt_h, tm_h = host[0], host[1], host[2], host[3]
+        hyper = Hyper(self.step_size, self.chara_lamb, self.chara_beta, self.min_step_frac, flow)
+        form = self._replace_form(sigma_h, sigma_host.numel() == 1, B, self.replace_mode, self.batched_replace)
+        if form is None:
+            return None
+        table_np = build_table(abt_h, ve_h, hyper, form[0], form[1])
+        active = n_steps if mean_half_dt(abt_h, hyper) > 0.0 else 0
+        shape = tuple(sigma_shape) if sigma_shape is not None else tuple(sigma_host.shape)
+        return {"table": torch.from_numpy(table_np).to(device), "t_model": torch.from_numpy(tm_h.copy()).to(device),
+                "sigma": sigma_host.to(device=device, dtype=torch.float32).reshape(shape), "active": int(active)}
+
+    def run_planned(self, x, item, y, nz, pm, dims, cbuf, plan, rng_state, model_options, seed):
+        """One wrapper call from a plan_item: no host read-back, no H2D copy, no generator access -- only kernel
+        launches and the model calls, i.e. capturable as part of a larger CUDA graph.  x is rewritten in place."""
+        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+            raise RuntimeError("planned LanPaint call needs a contiguous fp32 CUDA state tensor")
+        self.img_dim_size = x.ndim
+        out = torch.empty_like(x)
+        done = self._launch_sequence(x, y, nz, pm, dims, item["table"], item["t_model"], item["sigma"], cbuf, out,
+                                     item["active"], plan, False, model_options, seed, None, rng_state)
+        self.substeps_done += done
+        return out
+
     # ---- the launch sequence of one outer step (shared by the eager path and graph capture) ----
     def _launch_sequence(self, xm, y, nz, pm, dims, tab, t_model, sigma_dev, cbuf, out, active, plan, call_scaling,
                          model_options, seed, stopper, rng_state, euler_coef=None, skip_prologue=False,

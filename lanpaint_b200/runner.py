@@ -482,3 +482,126 @@ class GraphedJob:
                 x_out.copy_(self.x, non_blocking=True)
                 return x_out
             return self.x.clone()
+
+
+class SamplerGraphJob:
+    """ANY deterministic k-diffusion sampler around the per-sigma wrapper as ONE CUDA graph per job.
+
+    `runner.GraphedJob` owns the sampler loop, so it only serves Euler.  For the other samplers (heun, dpm_2,
+    dpmpp_2m, deis, res_multistep, ...) the loop is third-party Python that calls the wrapper with sigma values only
+    it knows.  But for a fixed schedule that sequence is deterministic: the node layer records it during the first,
+    eager job of a configuration (`KSamplerX0Inpaint.trace`), this class turns every recorded call into device
+    constants (`engine.plan_item`) and then runs the sampler function ITSELF under stream capture -- its Python runs
+    once, at capture -- with the wrapper serving the planned calls (`engine.run_planned`: no read-back, no copies).
+    The sampler gets the schedule as a CPU tensor so that its own scalar tests (`sigmas[i + 1] == 0`) stay on the host.
+    Falls back (exception -> the node layer uses the per-sigma graphs) when the sampler syncs, allocates host
+    memory in a way capture forbids, draws its own noise, or calls the model a different number of times.
+
+    Callbacks: the sampler's per-step callback runs at capture time only, so it is recorded there (step index,
+    denoised tensor, x tensor -- graph-owned buffers that stay valid) and delivered in order after every replay, the
+    same deferred form GraphedJob uses for short jobs."""
+
+    def __init__(self, engine, sampler_function, extra_options, sigmas_cpu: torch.Tensor, trace, shape, device):
+        from .engine import _DrawPlan
+        self.engine, self.fn, self.extra_options = engine, sampler_function, dict(extra_options or {})
+        self.sigmas = sigmas_cpu.detach().to("cpu", torch.float32)
+        self.trace = list(trace)            # [(sigma_host [B] CPU tensor, times tuple, n_eff)]
+        self.device, self.shape = torch.device(device), tuple(shape)
+        mk = lambda: torch.empty(self.shape, dtype=torch.float32, device=self.device)
+        self.x0, self.y, self.noise, self.c = mk(), mk(), mk(), mk()
+        self.mask = None
+        self.rng_state = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.items = None
+        self.graph = None
+        self.result = None
+        self.recorded = []                  # callbacks seen at capture: (i, denoised, x)
+        self.draws = 0
+        self.launches = self.model_calls = self.substeps = 0
+        self.captures = 0
+        self._plan_cls = _DrawPlan
+        self.timing, self.last_events = False, None
+
+    def _load(self, latent_image, noise, pm, x_init):
+        import numpy as np
+        from .engine import PackedMask
+        self.y.copy_(latent_image, non_blocking=True)
+        self.noise.copy_(noise, non_blocking=True)
+        self.x0.copy_(x_init, non_blocking=True)
+        if self.mask is None or self.mask.data.shape != pm.data.shape or (
+                self.mask.row_stride, self.mask.channel_stride) != (pm.row_stride, pm.channel_stride):
+            self.mask = PackedMask(torch.empty_like(pm.data), pm.row_stride, pm.channel_stride)
+            self.graph = None
+        self.mask.data.copy_(pm.data, non_blocking=True)
+        B = self.shape[0]
+        self.dims = _native.Dims(B, self.x0.numel() // B, int(np.prod(self.shape[2:])), self.mask.row_stride,
+                                 self.mask.channel_stride)
+
+    def _capture(self, model_k, extra_args, want_callbacks):
+        eng = self.engine
+        B = self.shape[0]
+        self.items = []
+        for sigma_host, times, n_eff in self.trace:
+            item = eng.plan_item(B, sigma_host, times, n_eff, self.device)
+            if item is None:
+                raise RuntimeError("noise_scaling is not a linear form")
+            self.items.append(item)
+        plan = self._plan_cls(eng.rng, self.x0, 1).relative()   # before capture: reads the generator once
+        counts = (eng.launches, eng.model_calls, eng.substeps_done)
+        state = {"pos": 0}
+        job = self
+
+        def planned(x, model_options, seed):
+            if state["pos"] >= len(job.items):
+                raise RuntimeError("the sampler called the model more often than in its recorded job")
+            item = job.items[state["pos"]]
+            state["pos"] += 1
+            return eng.run_planned(x, item, job.y, job.noise, job.mask, job.dims, job.c, plan, job.rng_state.data_ptr(),
+                                   model_options, seed)
+        model_k.planned_call = planned
+        self.recorded = []
+        k_callback = None
+        if want_callbacks:
+            k_callback = lambda d: job.recorded.append((d["i"], d["denoised"], d["x"]))  # noqa: E731
+        graph = torch.cuda.CUDAGraph()
+        cap_stream = torch.cuda.Stream(device=self.device)
+        cap_stream.wait_stream(torch.cuda.current_stream(self.device))
+        try:
+            with torch.cuda.graph(graph, stream=cap_stream):
+                self.result = self.fn(model_k, self.x0, self.sigmas, extra_args=extra_args, callback=k_callback,
+                                      disable=True, **self.extra_options)
+        finally:
+            model_k.planned_call = None
+        if state["pos"] != len(self.items):
+            raise RuntimeError("the sampler called the model less often than in its recorded job")
+        self.graph, self.draws = graph, plan.used
+        self.launches, self.model_calls = eng.launches - counts[0], eng.model_calls - counts[1]
+        self.substeps = eng.substeps_done - counts[2]
+        eng.launches, eng.model_calls, eng.substeps_done = counts
+        self.captures += 1
+
+    def run(self, model_k, extra_args, latent_image, noise, pm, x_init, callback=None):
+        """callback(i, denoised, x, total_steps): ComfyUI's; delivered after the replay, in the sampler's order."""
+        import numpy as np
+        eng = self.engine
+        with torch.cuda.device(self.device):
+            self._load(latent_image, noise, pm, x_init)
+            if self.graph is None:
+                self._capture(model_k, extra_args, callback is not None)
+            plan = self._plan_cls(eng.rng, self.x0, 1)
+            self.rng_state.copy_(torch.from_numpy(plan.state_words().view(np.int64)))
+            if self.timing:
+                self.last_events = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                self.last_events[0].record()
+            self.graph.replay()
+            if self.timing:
+                self.last_events[1].record()
+            plan.consume(self.draws)
+            plan.finish()
+            eng.launches += self.launches
+            eng.model_calls += self.model_calls
+            eng.substeps_done += self.substeps
+            if callback is not None:
+                total = len(self.sigmas) - 1
+                for i, den, xx in self.recorded:
+                    callback(i, den, xx, total)
+            return self.result.clone()

@@ -251,7 +251,26 @@ def sample_heun(model, x, sigmas, extra_args=None, callback=None, disable=None):
     return x
 
 
-_SAMPLER_FUNCTIONS = {"euler": sample_euler, "heun": sample_heun}
+@torch.no_grad()
+def sample_euler_ancestral(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1.0, s_noise=1.0):
+    """k-diffusion's ancestral Euler with its default noise sampler (torch.randn_like on the global generator)."""
+    extra_args = extra_args or {}
+    s_in = x.new_ones([x.shape[0]])
+    for i in range(len(sigmas) - 1):
+        denoised = model(x, sigmas[i] * s_in, **extra_args)
+        s_from, s_to = float(sigmas[i]), float(sigmas[i + 1])
+        s_up = min(s_to, eta * (s_to ** 2 * (s_from ** 2 - s_to ** 2) / s_from ** 2) ** 0.5) if s_to > 0 else 0.0
+        s_down = (s_to ** 2 - s_up ** 2) ** 0.5
+        if callback is not None:
+            callback({"x": x, "i": i, "sigma": sigmas[i], "sigma_hat": sigmas[i], "denoised": denoised})
+        d = (x - denoised) / _append_dims(sigmas[i] * s_in, x.ndim)
+        x = x + d * (s_down - s_from)
+        if s_to > 0:
+            x = x + torch.randn_like(x) * s_noise * s_up
+    return x
+
+
+_SAMPLER_FUNCTIONS = {"euler": sample_euler, "heun": sample_heun, "euler_ancestral": sample_euler_ancestral}
 
 
 class KSAMPLER:
@@ -504,7 +523,8 @@ def install(version: str = "0.6.0") -> None:
     comfy.__path__ = []
     comfy.utils = mod("comfy.utils", repeat_to_batch_size=repeat_to_batch_size, PROGRESS_BAR_ENABLED=False)
     samplers_all = ["calc_cond_batch", "cfg_function", "cast_to_load_options", "sampling_function", "CFGGuider",
-                    "KSAMPLER", "KSampler", "ksampler", "sampler_object", "KSamplerX0Inpaint", "sample_euler", "sample_heun"]
+                    "KSAMPLER", "KSampler", "ksampler", "sampler_object", "KSamplerX0Inpaint", "sample_euler", "sample_heun",
+                    "sample_euler_ancestral"]
     comfy.samplers = mod("comfy.samplers", **{k: getattr(me, k) for k in samplers_all}, __all__=samplers_all)
     comfy.sampler_helpers = mod("comfy.sampler_helpers", prepare_mask=prepare_mask, prepare_sampling=prepare_sampling,
                                 cleanup_models=cleanup_models)

@@ -336,7 +336,8 @@ def test_other_samplers_replay_one_graph_per_outer_step(cuda_device):
     calls = N.LAST_ENGINE["engine"].model_calls
     patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
     for k in range(3):
-        got, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, sampler="heun", steps=10, n=3)
+        got, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, sampler="heun", steps=10, n=3,
+                               opts={"sampler_graph": False})
         assert N.LAST_RUN["fused"] is False
         assert torch.equal(got, plain), k
         assert N.LAST_ENGINE["engine"].model_calls == calls
@@ -466,3 +467,50 @@ def test_a_real_torch_module_under_the_node_graphs(cuda_device):
     if tuple(prm.data_ptr() for prm in net.parameters()) != before:
         assert mode == "eager"
     assert max_rel(moved, fresh) <= 1e-5
+
+
+def test_whole_sampler_loop_as_one_graph(cuda_device):
+    """heun (a deterministic sampler that is not plain Euler): the first job records what the sampler asks the wrapper
+    for, the second captures k-diffusion's own loop -- its Python runs once -- into ONE graph, later jobs replay it.
+    Same latent as plain launches bit for bit, same number of model calls, every progress callback delivered."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    N._ENGINES.clear()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(5)
+    y = torch.randn(2, 4, 32, 32, generator=g)
+    noise_mask = (torch.rand(2, 1, 32, 32, generator=g) < 0.5).float()
+    plain, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False}, sampler="heun", steps=10, n=3)
+    calls = N.LAST_ENGINE["engine"].model_calls
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+    modes = []
+    for k in range(4):
+        before = minicomfy.PROGRESS["calls"]
+        got, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, sampler="heun", steps=10, n=3)
+        modes.append(N.LAST_RUN["mode"])
+        assert torch.equal(got, plain), (k, modes)
+        assert N.LAST_ENGINE["engine"].model_calls == calls
+        assert minicomfy.PROGRESS["calls"] - before == 10 and minicomfy.PROGRESS["last"] == (10, 10)
+    assert modes == [None, "sampler-graph", "sampler-graph", "sampler-graph"], modes
+    assert N.LAST_RUN["job"].captures == 1
+    # another seed: same graph, fresh noise image and randn stream
+    other, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, sampler="heun", steps=10, n=3, seed=99)
+    ref, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False}, sampler="heun", steps=10, n=3, seed=99)
+    assert N.LAST_RUN["mode"] is None and torch.equal(other, ref) and not torch.equal(other, plain)
+
+
+def test_a_sampler_that_draws_its_own_noise_is_not_captured(cuda_device):
+    """euler_ancestral calls torch.randn_like between wrapper calls: its generator consumption interleaves with the
+    engine's, so the loop is not captured as a whole; the per-call graphs serve it and the result equals plain launches."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    N._ENGINES.clear()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(7)
+    y = torch.randn(1, 4, 32, 32, generator=g)
+    noise_mask = (torch.rand(1, 1, 32, 32, generator=g) < 0.5).float()
+    plain, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False}, sampler="euler_ancestral", steps=8, n=3)
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+    for k in range(3):
+        got, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, sampler="euler_ancestral", steps=8, n=3)
+        assert N.LAST_RUN["mode"] is None and torch.equal(got, plain), k
