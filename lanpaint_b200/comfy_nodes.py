@@ -422,6 +422,7 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
             if sg_ok and isinstance(entry.trace, list):
                 samples = KSAMPLER._sampler_graph(self, model_k, entry, engine, x_init, latent_image, denoise_mask,
                                                   model_options, extra_args, callback, opts)
+                sg_ok = sg_ok and entry.trace is not False
         if samples is None:
             k_callback = None
             if callback is not None:
@@ -569,10 +570,14 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
             if callback is not None:     # callbacks can only be delivered after the replay: short jobs only
                 dev_ms = entry.eager_events[0].elapsed_time(entry.eager_events[1]) if entry.eager_events else None
                 nbytes = len(entry.trace) * x_init.numel() * 4
-                if not (opts.get("deferred_callbacks", True) and dev_ms is not None
-                        and dev_ms <= float(opts.get("deferred_max_ms", 50.0))
-                        and nbytes <= int(opts.get("deferred_max_bytes", 1 << 30))):
+                if not opts.get("deferred_callbacks", True) or nbytes > int(opts.get("deferred_max_bytes", 1 << 30)):
                     entry.trace = False
+                    return None
+                if dev_ms is None or dev_ms > float(opts.get("deferred_max_ms", 50.0)):
+                    # too long to be sure nobody watches the progress bar -- or the first job of the process, which
+                    # also paid CUDA's lazy module loading: record and time one more eager job before giving up
+                    entry.sg_retries += 1
+                    entry.trace = None if entry.sg_retries < 3 else False
                     return None
             job = entry.sampler_job = SamplerGraphJob(engine, self.sampler_function, self.extra_options,
                                                       torch.tensor(model_k.sigmas_host), entry.trace,
@@ -618,12 +623,13 @@ def _weights_fingerprint(model_wrap):
 
 class _EngineEntry:
     __slots__ = ("engine", "job", "runs", "graph_failed", "last_mode", "weights", "keep", "pinned", "eager_events",
-                 "trace", "sampler_job")
+                 "trace", "sampler_job", "sg_retries")
 
     def __init__(self):
         self.engine = self.job = None
         self.trace = None           # None: not recorded yet; list: the wrapper calls of one job; False: not capturable
         self.sampler_job = None
+        self.sg_retries = 0
         self.pinned = []
         self.eager_events = None   # CUDA events around the previous job: how long this configuration takes
         self.runs = 0
