@@ -514,7 +514,7 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
                 dev_ms = entry.eager_events[0].elapsed_time(entry.eager_events[1])
             deferred = (opts.get("deferred_callbacks", True) and dev_ms is not None
                         and dev_ms <= float(opts.get("deferred_max_ms", 50.0))
-                        and job.per_step_bytes() <= int(opts.get("deferred_max_bytes", 1 << 30)))
+                        and job.per_step_bytes() <= int(opts.get("deferred_max_bytes", 4 << 30)))
             mode = "job" if deferred else "steps"
         timing = None
         if entry is not None:
@@ -569,8 +569,9 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
         if job is None:
             if callback is not None:     # callbacks can only be delivered after the replay: short jobs only
                 dev_ms = entry.eager_events[0].elapsed_time(entry.eager_events[1]) if entry.eager_events else None
-                nbytes = len(entry.trace) * x_init.numel() * 4
-                if not opts.get("deferred_callbacks", True) or nbytes > int(opts.get("deferred_max_bytes", 1 << 30)):
+                # the recorded callbacks keep (denoised, x) of every step alive inside the graph's memory pool
+                nbytes = 2 * (len(model_k.sigmas_host) - 1) * x_init.numel() * 4
+                if not opts.get("deferred_callbacks", True) or nbytes > int(opts.get("deferred_max_bytes", 4 << 30)):
                     entry.trace = False
                     return None
                 if dev_ms is None or dev_ms > float(opts.get("deferred_max_ms", 50.0)):
