@@ -269,8 +269,8 @@ class Spec:
     """One benchmark configuration driven through LanPaint_KSampler.sample."""
 
     def __init__(self, name, batch, latent, n_inner=5, flow=False, shift=1.0, scheduler="karras", steps=N_OUTER,
-                 cfg=5.0, note=""):
-        self.name, self.batch, self.latent, self.n_inner = name, batch, tuple(latent), n_inner
+                 cfg=5.0, note="", sampler="euler"):
+        self.name, self.batch, self.latent, self.n_inner, self.sampler = name, batch, tuple(latent), n_inner, sampler
         self.flow, self.shift, self.scheduler, self.steps, self.cfg, self.note = flow, shift, scheduler, steps, cfg, note
 
     @property
@@ -324,10 +324,14 @@ class NodeWorkload:
         """One node call; returns (wall seconds, device ms of the sampler loop inside it)."""
         self.seed += 1
         t0 = time.perf_counter()
-        (out,) = self.node.sample(self.patcher, self.seed, self.spec.steps, self.spec.cfg, "euler", self.spec.scheduler,
-                                  0.3, -0.2, self.latent, 1.0, self.spec.n_inner, "Image First", "", self.N.IMAGE_MODE)
+        (out,) = self.node.sample(self.patcher, self.seed, self.spec.steps, self.spec.cfg, self.spec.sampler,
+                                  self.spec.scheduler, 0.3, -0.2, self.latent, 1.0, self.spec.n_inner, "Image First", "",
+                                  self.N.IMAGE_MODE)
         wall = time.perf_counter() - t0            # the result is a host tensor: the call has synchronised
         e0, e1 = self.N.LAST_RUN["events"]
+        if self.spec.sampler != "euler":           # other samplers evaluate the wrapper at sigmas of their own
+            eng = self.N.LAST_ENGINE["engine"]
+            self.substeps, self.guider_calls = eng.substeps_done, eng.model_calls
         self.last_out = out["samples"]
         return wall, e0.elapsed_time(e1)
 
@@ -341,7 +345,7 @@ class NodeWorkload:
             self.call()
             job = self.N.LAST_RUN.get("job")
             modes.append((self.N.LAST_RUN["mode"], job is not None and job.captures == before))
-            if len(modes) >= 2 and modes[-1] == modes[-2] and modes[-1][1] and modes[-1][0] != "eager":
+            if len(modes) >= 2 and modes[-1] == modes[-2] and modes[-1][1] and modes[-1][0] not in ("eager", None):
                 break
         return self.N.LAST_RUN["mode"]
 
@@ -668,6 +672,19 @@ def run_b200(args):
             configs.append(c)
             torch.cuda.empty_cache()
 
+    # ---- another sampler through the same node: k-diffusion's own loop captured as one graph ---------------------
+    other_sampler = None
+    if args.configs and not args.quick and world == 1:
+        rec, wl = measure(Spec("sdxl_batch_heun", R, SHAPE, sampler="heun"), args.rng, 1, 0, 8, seed=rank + 7)
+        other_sampler = {"sampler": "heun", "requests_per_gpu": R, "value": rec["value"],
+                         "ms_per_job_device": rec["ms_per_job_device"], "e2e_value": rec["e2e_value"],
+                         "substeps_per_request": rec["substeps_per_request"],
+                         "guider_calls_per_request": rec["guider_calls_per_request"], "launch": rec["launch"],
+                         "note": "heun evaluates the wrapper twice per step; its whole loop (k-diffusion's Python) is captured "
+                                 "into one CUDA graph after an eager first job recorded the sigma sequence"}
+        del wl
+        torch.cuda.empty_cache()
+
     # ---- cfg5 frame-sharded synthetic run: one sample's frames split over the ranks ------------------------------
     frame_shard = None
     if args.frame_shard and not args.quick:
@@ -703,7 +720,7 @@ def run_b200(args):
             "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg, "roofline": roof, "rooflines": roofs, "cpu_baseline": cpu, "e2e": e2e,
-            "variants": variants, "serving": serving, "frame_shard": frame_shard,
+            "variants": variants, "serving": serving, "frame_shard": frame_shard, "other_sampler": other_sampler,
             "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

@@ -240,7 +240,7 @@ def test_node_default_is_graph_replay_and_matches_oracle(cuda_device):
     for deferred, want_modes, want_captures in ((False, ["eager", "steps", "steps", "steps"], 20),
                                                 (True, ["eager", "job", "job", "job"], 1)):
         # a job this short (a pointwise network) runs as ONE graph with the callbacks delivered right after it;
-        # {"deferred_callbacks": False} -- or a job longer than 20 ms, i.e. any real network -- keeps one graph per
+        # {"deferred_callbacks": False} -- or a job longer than 50 ms, i.e. any real network -- keeps one graph per
         # outer step with the callback between them
         patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
         modes = []
