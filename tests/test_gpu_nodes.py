@@ -167,6 +167,20 @@ def test_nodes_run_under_inference_mode(cuda_device):
     with torch.inference_mode():
         inf = run()
     assert torch.equal(plain, inf.clone())
+    # and the graph-replayed path entirely under inference mode (static buffers, capture and replay all created there)
+    N._ENGINES.clear()
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(_denoiser), dev)
+    with torch.inference_mode():
+        outs, modes = [], []
+        for _ in range(4):
+            (out,) = N.LanPaint_KSampler().sample(patcher, 5, 8, 4.0, "euler", "karras", 0.3, -0.2,
+                                                  {"samples": y, "noise_mask": noise_mask}, 1.0, 3, "Image First", "",
+                                                  N.IMAGE_MODE)
+            outs.append(out["samples"].clone())
+            modes.append(N.LAST_RUN["mode"])
+    assert modes[0] == "eager" and modes[-1] in ("steps", "job"), modes
+    for o in outs:
+        assert torch.equal(o, plain)
 
 
 def test_flux_type_model_runs_on_the_flow_schedule(cuda_device):
