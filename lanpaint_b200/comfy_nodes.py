@@ -340,14 +340,16 @@ class KSamplerX0Inpaint:
 class KSAMPLER(comfy.samplers.KSAMPLER):
     """KSAMPLER.sample replacement (nodes.py:318-379): builds the per-sigma wrapper and the engine.
 
-    Two launch strategies behind the same call:
+    Three launch strategies behind the same call:
       * the sampler is plain Euler (what the node recommends) and nothing needs host code inside an outer
         step: the whole sampler loop is run by `runner.GraphedJob` -- host-computed schedule, Euler update and
-        next replace step fused into the step-boundary kernel, CUDA graphs (one per outer step when ComfyUI
-        passed a progress/preview callback, one for the whole job otherwise) cached across sample() calls;
-      * anything else (the other 21 samplers, early stop, AV packs, mask schedules): k-diffusion's own loop
-        calls the per-sigma wrapper, which replays one CUDA graph per outer step.
-    Either way the first job of a configuration launches eagerly and the graphs are captured when the same
+        next replace step fused into the step-boundary kernel, CUDA graphs (one per job, or one per outer step
+        with ComfyUI's callback between them when the job is long enough to watch) cached across sample() calls;
+      * any other deterministic sampler: the first job records which sigmas the sampler hands the wrapper, then
+        k-diffusion's sampler function itself is captured into ONE graph (`runner.SamplerGraphJob`);
+      * anything else (samplers that draw their own noise, early stop, AV packs, mask schedules): k-diffusion's own
+        loop calls the per-sigma wrapper, which replays one CUDA graph per outer step.
+    In every case the first job of a configuration launches eagerly and the graphs are captured when the same
     configuration comes back, so no model evaluation is ever spent on a warm-up pass."""
 
     def sample(self, model_wrap, sigmas, extra_args, callback, noise, latent_image=None, denoise_mask=None,
@@ -436,11 +438,14 @@ class KSAMPLER(comfy.samplers.KSAMPLER):
                 off0 = gen.get_offset()
                 t_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 t_ev[0].record()
-            samples = self.sampler_function(model_k, x_init, sigmas, extra_args=extra_args, callback=k_callback,
-                                            disable=disable_pbar, **self.extra_options)
+            try:
+                samples = self.sampler_function(model_k, x_init, sigmas, extra_args=extra_args, callback=k_callback,
+                                                disable=disable_pbar, **self.extra_options)
+            finally:
+                if recording:
+                    engine.cuda_graph = use_graph
             if recording:
                 t_ev[1].record()
-                engine.cuda_graph = use_graph
                 own_draws = (gen.get_offset() - off0) != model_k.rng_delta     # the sampler drew noise itself
                 entry.trace = False if (own_draws or not model_k.trace) else model_k.trace
                 entry.eager_events = t_ev
