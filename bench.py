@@ -149,6 +149,47 @@ def reference_engine_kind():
     return "reference" if build_ref.load() is not None else "port"
 
 
+def reference_nodes():
+    """The reference's own node module (oracle/_ref bytecode of nodes.py, imported over minicomfy) or None."""
+    from oracle import build_ref
+    return build_ref.load_nodes()
+
+
+REFERENCE_API = ("the reference's own LanPaint_KSampler.sample (oracle/_ref bytecode of nodes.py + lanpaint.py, ComfyUI "
+                 "replaced by minicomfy as in the GPU arm), LATENT dict in -> LATENT dict out")
+
+
+def cpu_node_job(ref_nodes, requests: int, threads: int, seed: int = 0):
+    """ONE call of the UNMODIFIED reference's `LanPaint_KSampler.sample` on `requests` requests on the host cores:
+    the very call the GPU arm times (same arguments, same conditioning, euler / karras-20 / N=5, the synthetic
+    network as its torch formula), through the reference's own patched CFGGuider / KSAMPLER / per-sigma wrapper
+    (nodes.py:161-216, 229-379, 487-513) into `LanPaint.__call__`.  ComfyUI's CPU prepare_noise and the LATENT
+    dict hand-over are inside the timed region, as they are in the GPU arm's e2e.
+    Returns (seconds, request-sub-steps done)."""
+    import contextlib
+    import io
+    import minicomfy
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(seed)
+    y = torch.randn((requests,) + SHAPE, generator=g)
+    nm = (torch.rand((requests, 1) + SHAPE[1:], generator=g) < 0.5).float()
+    calls = [0]
+
+    def net(x, sigma, cond):        # lanpaint_b200.runner.SynthCondNet's formula (lp_synth_denoiser_f32)
+        calls[0] += 1
+        return 0.7 * x + 0.1 * torch.tanh(x) + float(cond)
+
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(net), "cpu")
+    node = ref_nodes.NODE_CLASS_MAPPINGS["LanPaint_KSampler"]()
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):      # the reference prints from outer_sample (nodes.py:179)
+        (out,) = node.sample(patcher, 1000 + seed, N_OUTER, 5.0, "euler", "karras", 0.3, -0.2,
+                             {"samples": y, "noise_mask": nm}, 1.0, N_INNER, "Image First", "", "🖼️ Image Inpainting")
+    dt = time.perf_counter() - t0
+    assert calls[0] == 2 * 73 and out["samples"].shape == y.shape, (calls[0], out["samples"].shape)
+    return dt, requests * 53
+
+
 def calibrate_threads(requests: int) -> int:
     """The reference's eager path is ~90 small element-wise ops per sub-step; on a many-core host more
     threads can be much slower (fork/join per op).  Time ONE outer step of the actual workload (5 sub-steps,
@@ -212,18 +253,27 @@ def run_reference(args):
     host_cores = os.cpu_count() or 1
     req = args.ref_requests
     kind = reference_engine_kind()
+    ref_nodes = reference_nodes() if kind == "reference" else None
     cores = calibrate_threads(req)
-    for _ in range(args.warmup):
-        cpu_job(req, N_OUTER, cores)
+
+    def job(seed):
+        if ref_nodes is not None:
+            return cpu_node_job(ref_nodes, req, cores, seed)
+        return cpu_job(req, N_OUTER, cores, seed)
+
+    for k in range(args.warmup):
+        job(k)
     t, units = 0.0, 0
-    for _ in range(args.steps):
-        dt, u = cpu_job(req, N_OUTER, cores)
+    for k in range(args.steps):
+        dt, u = job(100 + k)
         t += dt
         units += u
     value = units / t
     sample = (f"{req} requests per step (the GPU arm batches {args.requests} per call), full karras-20 x N=5 schedule "
-              f"(53 sub-steps/request); {cores} torch threads (fastest of a probe over 1..{host_cores} host cores); engine = "
-              + ("the reference's own LanPaint.__call__ (oracle/_ref bytecode)" if kind == "reference" else "oracle port"))
+              f"(53 sub-steps/request); {cores} torch threads (fastest of a probe over 1..{host_cores} host cores); "
+              + (REFERENCE_API if ref_nodes is not None else
+                 "engine = the reference's own LanPaint.__call__ (oracle/_ref bytecode) under the oracle's Euler loop"
+                 if kind == "reference" else "oracle port"))
     cfg = workload_config(args, "reference")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "sub-steps/s", "n_gpus": args.gpus,
@@ -234,6 +284,9 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "sub-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if ref_nodes is not None:
+        line["config"]["api"] = REFERENCE_API
+        line["e2e"]["api"] = REFERENCE_API
     print(json.dumps(line), flush=True)
 
 
@@ -697,14 +750,20 @@ def run_b200(args):
         warnings.filterwarnings("ignore")
         host_cores = os.cpu_count() or 1
         kind = reference_engine_kind()
+        ref_nodes = reference_nodes() if kind == "reference" else None
         cores = calibrate_threads(args.ref_requests)
         cpu_job(2, 2, cores)  # warm
-        dt, u = cpu_job(args.ref_requests, N_OUTER, cores)
+        if ref_nodes is not None:
+            dt, u = cpu_node_job(ref_nodes, args.ref_requests, cores)
+        else:
+            dt, u = cpu_job(args.ref_requests, N_OUTER, cores)
         cpu = {"value": u / dt, "unit": "sub-steps/s", "cores": cores, "kind": kind,
                "same_reference_math_on_this_gpu": eager_reference_on_gpu(Spec("sdxl_batch8", args.ref_requests, SHAPE), dev),
                "sample": f"{args.ref_requests} of {R} requests, full karras-20 x N=5 schedule, {dt:.1f} s of CPU work; "
-                         f"{cores} torch threads (fastest of a probe over 1..{host_cores} host cores); engine = "
-                         + ("the reference's own LanPaint.__call__ (oracle/_ref bytecode)" if kind == "reference" else "oracle port")}
+                         f"{cores} torch threads (fastest of a probe over 1..{host_cores} host cores); "
+                         + (REFERENCE_API if ref_nodes is not None else
+                            "engine = the reference's own LanPaint.__call__ (oracle/_ref bytecode)" if kind == "reference"
+                            else "oracle port")}
 
     clocks.stop()
     if rank == 0:

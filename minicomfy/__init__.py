@@ -465,7 +465,8 @@ def common_ksampler(model, seed, steps, cfg, sampler_name, scheduler, positive, 
     if disable_noise:
         noise = torch.zeros(latent_image.size(), dtype=latent_image.dtype, layout=latent_image.layout, device="cpu")
     else:
-        noise = prepare_noise(latent_image, seed, latent.get("batch_index"))
+        # through the module, like ComfyUI's nodes.py (`comfy.sample.prepare_noise(...)`): a patched one is honoured
+        noise = sys.modules["comfy.sample"].prepare_noise(latent_image, seed, latent.get("batch_index"))
     noise_mask = latent.get("noise_mask")
     # like ComfyUI: there is always a callback (progress bar; a preview only when a previewer is configured)
     callback = sys.modules["latent_preview"].prepare_callback(model, steps)

@@ -23,7 +23,12 @@ def test_reference_arm_prints_one_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] > 0 and "sample" in cb
     assert d["config"]["reference_requests"] == 2
-    assert d["e2e"] == {"value": d["value"], "unit": "sub-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    e2e = dict(d["e2e"])
+    api = e2e.pop("api", None)
+    assert e2e == {"value": d["value"], "unit": "sub-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    if cb["kind"] == "reference":      # oracle/_ref built: the arm is the reference's own node call, like the GPU arm's
+        assert "LanPaint_KSampler.sample" in api and "LanPaint_KSampler.sample" in cb["sample"]
+        assert d["config"]["api"] == api
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():

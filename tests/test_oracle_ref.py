@@ -30,3 +30,38 @@ def test_reference_bytecode_equals_the_port(flow, n, batch, monkeypatch):
     xr = x.clone()
     out = eng(xr, y, noise, sigma, mask, tuple(times), {}, 0, n_steps=n)
     assert torch.equal(out, want_out) and torch.equal(xr, want_x)
+
+
+def test_reference_bytecode_node_layer_reproduces_the_node_goldens(monkeypatch):
+    """oracle/_ref's node layer (what `bench.py --impl reference` calls) is the code that wrote tests/golden/node_*.npz:
+    the same call on this host reproduces a fixture (to fp32 round-off: the host's tanh may differ by an ulp from the
+    build container's)."""
+    import contextlib
+    import io
+    import json
+    import os
+    import sys
+
+    import numpy as np
+
+    from _node_cases import build_patcher, call_node
+    from conftest import GOLDEN_DIR
+    ref_nodes = build_ref.load_nodes()
+    if ref_nodes is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference: `make -C oracle`)")
+    assert ref_nodes.__file__.endswith(".pyc")
+    for name in ("node_ksampler_prompt_first_batch2", "node_advanced_window_leftover", "node_custom_random_noise"):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        c = json.loads(str(z["meta"]))
+        replay = iter(torch.from_numpy(t.astype(np.float32)) for t in z["tape"])
+        monkeypatch.setattr(torch, "randn_like", lambda t, **kw: next(replay).to(t.dtype))
+        if "noise_image" in z.files:
+            image = torch.from_numpy(z["noise_image"])
+            monkeypatch.setattr(sys.modules["comfy.sample"], "prepare_noise", lambda *a, **k: image.clone())
+        latent = {"samples": torch.from_numpy(z["samples"]),
+                  "noise_mask": torch.from_numpy(z["noise_mask"].astype(np.float32))}
+        with contextlib.redirect_stdout(io.StringIO()):
+            outs = call_node(ref_nodes, c, build_patcher(c), latent)
+        want = torch.from_numpy(z["out"])
+        assert float((outs[0]["samples"] - want).abs().max() / want.abs().max()) <= 1e-6
+        assert next(replay, None) is None, "the reference consumed fewer draws than the fixture holds"
