@@ -322,9 +322,11 @@ class Spec:
     """One benchmark configuration driven through LanPaint_KSampler.sample."""
 
     def __init__(self, name, batch, latent, n_inner=5, flow=False, shift=1.0, scheduler="karras", steps=N_OUTER,
-                 cfg=5.0, note="", sampler="euler"):
+                 cfg=5.0, note="", sampler="euler", network=None, model_type=None):
         self.name, self.batch, self.latent, self.n_inner, self.sampler = name, batch, tuple(latent), n_inner, sampler
         self.flow, self.shift, self.scheduler, self.steps, self.cfg, self.note = flow, shift, scheduler, steps, cfg, note
+        self.network = network          # None: the pointwise synthetic network; else a torch module (minicomfy.networks)
+        self.model_type = model_type    # None: FLOW / EPS from `flow`; "FLUX" sets cfg_BIG = 1 like the reference does
 
     @property
     def shape(self):
@@ -356,8 +358,9 @@ class NodeWorkload:
         else:                                           # rand(B,1,*spatial) per site; 1 = regenerate
             nm = (torch.rand(mshape, generator=g) < 0.5).float()
         self.latent = {"samples": y.pin_memory(), "noise_mask": nm.pin_memory()}
-        mtype = minicomfy.ModelType.FLOW if spec.flow else minicomfy.ModelType.EPS
-        self.net = SynthCondNet()
+        mtype = (getattr(minicomfy.ModelType, spec.model_type) if spec.model_type else
+                 minicomfy.ModelType.FLOW if spec.flow else minicomfy.ModelType.EPS)
+        self.net = spec.network if spec.network is not None else SynthCondNet()
         self.patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(self.net, model_type=mtype, latent_channels=shape[1],
                                                                  shift=spec.shift), dev)
         opts = {"rng": rng, "timing": True}
@@ -738,6 +741,14 @@ def run_b200(args):
         del wl
         torch.cuda.empty_cache()
 
+    # ---- cfg4 with a real PyTorch network captured in the graphs -------------------------------------------------
+    real_network = None
+    if args.real_network and not args.quick and world == 1:
+        try:
+            real_network = run_real_network(dev, args)
+        except Exception as e:   # an informational record never breaks the bench line
+            real_network = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- cfg5 frame-sharded synthetic run: one sample's frames split over the ranks ------------------------------
     frame_shard = None
     if args.frame_shard and not args.quick:
@@ -780,15 +791,17 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg, "roofline": roof, "rooflines": roofs, "cpu_baseline": cpu, "e2e": e2e,
             "variants": variants, "serving": serving, "frame_shard": frame_shard, "other_sampler": other_sampler,
+            "real_network": real_network,
             "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
     group.close()
 
 
-def eager_reference_on_gpu(spec: Spec, dev):
+def eager_reference_on_gpu(spec: Spec, dev, model=None):
     """The reference's math (oracle port, op for op) with device="cuda": what a user of the reference runs today on
-    this very GPU (eager PyTorch, ~89 element-wise launches per sub-step).  Informational, not the reference arm."""
+    this very GPU (eager PyTorch, ~89 element-wise launches per sub-step).  Informational, not the reference arm.
+    `model`: a guider double around a real network (default: the oracle's pointwise two-head network)."""
     try:
         from oracle import langevin_oracle as O
         import minicomfy
@@ -805,16 +818,108 @@ def eager_reference_on_gpu(spec: Spec, dev):
             sampling = O.VESampling()
         hp = O.Hyper(n_steps=spec.n_inner, min_step_frac=1.0, flow=spec.flow)
         cnt = {}
-        O.euler_inpaint(O.PointwiseDenoiser(sampling), y, noise, dm, sig, hp, counters=cnt)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        O.euler_inpaint(O.PointwiseDenoiser(sampling), y, noise, dm, sig, hp, counters=cnt)
-        torch.cuda.synchronize()
+        if model is None:
+            model = O.PointwiseDenoiser(sampling)
+        else:
+            model.model_sampling = sampling
+        with torch.no_grad():
+            O.euler_inpaint(model, y, noise, dm, sig, hp, counters=cnt)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            O.euler_inpaint(model, y, noise, dm, sig, hp, counters=cnt)
+            torch.cuda.synchronize()
         tq = time.perf_counter() - t0
         return {"value": shape[0] * cnt["substeps"] / tq, "unit": "sub-steps/s", "requests": shape[0],
                 "ms_per_job": 1e3 * tq, "what": "oracle port, device=cuda, eager launches, same schedule"}
     except Exception as e:  # never let the informational leg break the bench line
         return {"error": f"{type(e).__name__}: {e}"}
+
+
+class NetworkGuider:
+    """What the reference's patched CFGGuider hands its engine when cfg == 1 (Flux: uncond skipped, cfg_BIG = 1):
+    both heads are the one conditional evaluation of the network (nodes.py:161-175, 331-334)."""
+
+    def __init__(self, net, cond):
+        self.inner_model, self.model_sampling, self.net, self.cond = self, None, net, cond
+
+    def __call__(self, x, t, model_options=None, seed=None):
+        out = self.net(x, t, self.cond)
+        return out, out
+
+
+def run_real_network(dev, args):
+    """BASELINE configs[3] with a real PyTorch network in the loop: a Flux-shaped bf16 DiT stand-in (random weights;
+    minicomfy.networks.DiTStandIn) behind `LanPaint_KSampler.sample`, [1,16,128,128] latent, flow simple-20 x N=5,
+    cfg 1 (52 sub-steps, 72 forwards per job).  The node path captures the network together with the update kernels
+    (north_star: "CUDA-graph-captured once per (shape, sigma) and replayed inside the inner loop"); reported next to
+    plain launches of the same path and to the reference's math run eagerly around the same network on this GPU."""
+    from minicomfy.networks import DiTStandIn
+    torch.manual_seed(1234)
+    net = DiTStandIn().to(dev).eval()
+    spec = Spec("cfg4_flux_dit", 1, (16, 128, 128), flow=True, shift=1.15, scheduler="simple", cfg=1.0,
+                network=net, model_type="FLUX")
+    out = {"network": f"minicomfy.networks.DiTStandIn: 2x2 patchify -> 4096 tokens, hidden {net.hidden}, "
+                      f"{len(net.blocks)} adaLN blocks, bf16 SDPA attention, {net.n_params() / 1e6:.0f} M random-init parameters, "
+                      "x0 = x - sigma * v in fp32 (ComfyUI's calculate_denoised)",
+           "latent": [1, 16, 128, 128], "schedule": "flow simple-20 shift 1.15, N=5, cfg 1.0 (uncond skipped, cfg_BIG = 1)"}
+    with torch.no_grad():
+        x = torch.randn(1, 16, 128, 128, device=dev)
+        t = torch.full((1,), 0.5, device=dev)
+        for _ in range(3):
+            net(x, t, 0.3)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            net(x, t, 0.3)
+        e1.record()
+        e1.synchronize()
+        out["network_forward_ms_eager"] = e0.elapsed_time(e1) / 10
+        # the same ten forwards as one CUDA graph: what a forward costs inside the captured job
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(10):
+                    net(x, t, 0.3)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph.replay()
+        e0.record()
+        graph.replay()
+        e1.record()
+        e1.synchronize()
+        fwd_ms = e0.elapsed_time(e1) / 10
+        out["network_forward_ms_graph_replay"] = fwd_ms
+        del graph
+        for key, opts in (("graph_replay", {}), ("plain_launches", {"cuda_graph": False})):
+            wl = NodeWorkload(spec, dev, args.rng, seed=5, extra_opts=opts)
+            for _ in range(3):          # eager -> capture -> replay
+                wl.call()
+            n, wall, span = 3, 0.0, 0.0
+            for _ in range(n):
+                w_, s_ = wl.call()
+                wall += w_
+                span += s_
+            st = wl.stats()
+            st.pop("graph_nodes_per_job", None)      # that count assumes the one-kernel synthetic network
+            out[key] = {"ms_per_job_device": span / n, "ms_per_job_wall": 1e3 * wall / n, "launch": st,
+                        "substeps": wl.substeps, "network_forwards": wl.guider_calls,
+                        "substeps_per_s": wl.substeps / (span / n * 1e-3)}
+            del wl
+        calls0 = net.calls
+        out["reference_math_eager_on_this_gpu"] = eager_reference_on_gpu(spec, dev, NetworkGuider(net, 0.3))
+        out["reference_math_eager_on_this_gpu"]["network_forwards_per_job"] = (net.calls - calls0) // 2
+    g = out["graph_replay"]
+    out["update_path_share_of_job"] = max(0.0, 1.0 - g["network_forwards"] * fwd_ms / g["ms_per_job_device"])
+    ref = out["reference_math_eager_on_this_gpu"]
+    if "ms_per_job" in ref:
+        out["speedup_vs_reference_math_eager"] = ref["ms_per_job"] / g["ms_per_job_wall"]
+        out["note"] = ("with a real network the job is the network: the update path's share is what is left after "
+                       "network_forwards x network_forward_ms_graph_replay; the reference spends its extra time on ~89 eager launches "
+                       "per sub-step and 2 + N + 1 host read-backs per outer step")
+    del net
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_frame_shard(group, dev, args):
@@ -850,6 +955,8 @@ def main():
     ap.add_argument("--no-configs", dest="configs", action="store_false", help="skip the BASELINE configuration records")
     ap.add_argument("--no-kernel-timer", dest="kernel_timer", action="store_false")
     ap.add_argument("--no-frame-shard", dest="frame_shard", action="store_false")
+    ap.add_argument("--no-real-network", dest="real_network", action="store_false",
+                    help="skip the cfg4 record with the bf16 DiT stand-in in the loop")
     ap.add_argument("--frame-shard-threshold", type=float, default=0.05,
                     help="InnerThreshold of the frame-sharded record that runs with the early stopper on")
     ap.add_argument("--mask", default="random", choices=["random", "blob"],

@@ -28,6 +28,9 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--requests", type=int, nargs="+", default=[1, 8, 128])
 ap.add_argument("--rng", default="torch")
 ap.add_argument("--jobs", type=int, default=5)
+ap.add_argument("--network", default="synth", choices=["synth", "dit"],
+                help="synth: the one-kernel pointwise network on SDXL [R,4,128,128]; dit: the bf16 DiT stand-in "
+                     "(minicomfy.networks) on the Flux-shaped [R,16,128,128] latent, flow simple-20, cfg 1")
 ap.add_argument("--no-callback", action="store_true", help="call the guider without a progress callback: whole-job graph")
 ap.add_argument("--per-step", action="store_true",
                 help="one graph per outer step with the callback between them even for short jobs (deferred_callbacks=False)")
@@ -72,16 +75,25 @@ print(f"# torch.profiler (CUPTI) timeline of the sampler loop, node API, rng={ar
 print("# requests  job  kernels  span_us  busy_us  gap_%   largest_idle_us")
 for R in args.requests:
     g = torch.Generator().manual_seed(0)
-    y = torch.randn(R, 4, 128, 128, generator=g)
+    dit = args.network == "dit"
+    y = torch.randn(R, 16 if dit else 4, 128, 128, generator=g)
     noise_mask = (torch.rand(R, 1, 128, 128, generator=g) < 0.5).float()
-    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(SynthCondNet()), dev)
+    if dit:
+        from minicomfy.networks import DiTStandIn
+        torch.manual_seed(1234)
+        base = minicomfy.BaseModel(DiTStandIn().to(dev).eval(), model_type=minicomfy.ModelType.FLUX, latent_channels=16,
+                                   shift=1.15)
+    else:
+        base = minicomfy.BaseModel(SynthCondNet())
+    patcher = minicomfy.ModelPatcher(base, dev)
     patcher.model_options["lanpaint_b200"] = {"rng": args.rng, "deferred_callbacks": not args.per_step}
     node = N.LanPaint_KSampler()
 
     def call(seed):
         if not args.no_callback:
-            return node.sample(patcher, seed, 20, 5.0, "euler", "karras", 0.3, -0.2, {"samples": y, "noise_mask": noise_mask},
-                               1.0, 5, "Image First", "", N.IMAGE_MODE)
+            with torch.no_grad():
+                return node.sample(patcher, seed, 20, 1.0 if dit else 5.0, "euler", "simple" if dit else "karras", 0.3, -0.2,
+                                   {"samples": y, "noise_mask": noise_mask}, 1.0, 5, "Image First", "", N.IMAGE_MODE)
         N._set_hyper(patcher, num_steps=5, cfg=5.0, prompt_mode="Image First")
         guider = minicomfy.CFGGuider(patcher)
         guider.set_conds(0.3, -0.2)

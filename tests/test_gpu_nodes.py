@@ -528,3 +528,51 @@ def test_a_sampler_that_draws_its_own_noise_is_not_captured(cuda_device):
     for k in range(3):
         got, _ = _ksampler_run(N, dev, y, noise_mask, patcher=patcher, sampler="euler_ancestral", steps=8, n=3)
         assert N.LAST_RUN["mode"] is None and torch.equal(got, plain), k
+
+
+def test_flux_shaped_transformer_under_the_node_graphs(cuda_device):
+    """BASELINE configs[3] in miniature: a Flux-type model (cfg 1 -> uncond skipped, cfg_BIG = 1, flow `simple`
+    schedule) whose network is a transformer (minicomfy.networks.DiTStandIn: patchify, adaLN blocks, SDPA attention)
+    captured in the node path's graphs.  Eager first job, captured second, replayed third: each equals the oracle's
+    restatement of the reference run around the same network with the same seed."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    from minicomfy.networks import DiTStandIn
+    N._ENGINES.clear()
+    dev = cuda_device
+    torch.manual_seed(0)
+    net = DiTStandIn(in_ch=16, hidden=128, depth=2, heads=4, dtype=torch.float32).to(dev).eval()
+    g = torch.Generator().manual_seed(12)
+    y = torch.randn(1, 16, 16, 16, generator=g)
+    noise_mask = (torch.rand(1, 1, 16, 16, generator=g) < 0.5).float()
+    base = minicomfy.BaseModel(net, model_type=minicomfy.ModelType.FLUX, latent_channels=16, shift=1.15)
+    patcher = minicomfy.ModelPatcher(base, dev)
+    outs, modes = [], []
+    with torch.no_grad():
+        for _ in range(3):
+            (out,) = N.LanPaint_KSampler().sample(patcher, 21, 10, 1.0, "euler", "simple", 0.3, -0.2,
+                                                  {"samples": y, "noise_mask": noise_mask}, 1.0, 3, "Image First", "",
+                                                  N.IMAGE_MODE)
+            outs.append(out["samples"])
+            modes.append(N.LAST_RUN["mode"])
+        eng = N.LAST_ENGINE["engine"]
+        assert modes[0] == "eager" and modes[-1] in ("steps", "job"), modes
+        assert float(patcher.LanPaint_cfg_BIG) == 1.0 or eng.IS_FLUX        # nodes.py:331-334: Flux runs with cfg_BIG = 1
+
+        class Guider:       # cfg == 1: one conditional evaluation serves both heads (nodes.py:161-175)
+            def __init__(self):
+                self.inner_model, self.model_sampling, self.calls = self, O.FlowSampling(), 0
+
+            def __call__(self, x, t, model_options=None, seed=None):
+                self.calls += 1
+                o = net(x, t, 0.3)
+                return o, o
+        noise = minicomfy.prepare_noise(y, 21)      # re-seeds every generator exactly like the node call did
+        sig = minicomfy.KSampler(patcher, 10, dev, "euler", "simple").sigmas.to(dev)
+        model = Guider()
+        want = O.euler_inpaint(model, y.to(dev), noise.to(dev), noise_mask.expand(1, 16, 16, 16).to(dev), sig,
+                               O.Hyper(n_steps=3, min_step_frac=1.0, flow=True))
+        want = base.model_sampling.inverse_noise_scaling(sig[-1], want)
+    assert eng.model_calls == model.calls
+    for o in outs:
+        assert max_rel(o, want) <= 1e-4, max_rel(o, want)
