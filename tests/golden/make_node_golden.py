@@ -95,6 +95,10 @@ CASES = [
     dict(name="node_custom_advanced", node="LanPaint_SamplerCustomAdvanced", shape=(1, 4, 8, 8), mask=(1, 1, 8, 8),
          args=dict(noise_seed=23, cfg=4.0, sampler="euler", sigmas=("karras", 8), LanPaint_NumSteps=3,
                    LanPaint_Lambda=6.0, LanPaint_StepSize=0.25, LanPaint_PromptMode="Prompt First")),
+    # MiniMax-H3 AV flat pack [1, C, video_n + audio_n]: the audio rows run on their own shifted sigma schedule
+    dict(name="node_av_flat_pack", node="outer_sample_av_pack", shape=(1, 8, 128), mask=(1, 8, 128), model_type="FLOW",
+         args=dict(seed=2, cfg=1.0, sigmas=[0.95, 0.8, 0.6, 0.4, 0.2, 0.0], LanPaint_NumSteps=3, n_video=96, n_audio=32,
+                   shift_video=3.0, shift_audio=1.5)),
 ]
 
 
@@ -131,8 +135,8 @@ def main():
             return noise_images[-1]
 
         fixed = None
-        if c["node"] == "LanPaint_SamplerCustomAdvanced":
-            fixed = torch.randn(c["shape"], generator=torch.Generator().manual_seed(c["args"]["noise_seed"]))
+        if c["node"] in ("LanPaint_SamplerCustomAdvanced", "outer_sample_av_pack"):
+            fixed = torch.randn(c["shape"], generator=torch.Generator().manual_seed(c["args"].get("noise_seed", 77)))
             noise_images.append(fixed)
         sys.modules["comfy.sample"].prepare_noise = prepare_noise
         try:

@@ -7,7 +7,9 @@ stream (and as `torch.randn_like` for the draws the node layer / an ancestral sa
 compared is everything between the two LATENT dicts: mask preparation, noise scaling, the sigma -> (VE, abt, t)
 glue, the inner-step ramp, dual CFG, the fused update kernels, the sampler's own steps and the epilogue
 (nodes.py:161-216, 229-379, 487-513).  Tolerance: the north_star contract (1e-3 of the final latent's scale)
-with the measured figure well below it (the network stand-in's tanh differs by an ulp between CPU and GPU)."""
+with the measured figure (<= 4.6e-7 on B200) asserted at 5e-6 (the network stand-in's tanh differs by an ulp between
+CPU and GPU).  `node_av_flat_pack` enters at the patched CFGGuider.outer_sample with `latent_shapes`, the way ComfyUI
+hands over a nested (video, audio) latent (MiniMax-H3: audio rows on their own shifted sigma schedule)."""
 import glob
 import json
 import os
@@ -27,7 +29,7 @@ pytestmark = pytest.mark.gpu
 
 NODE_CASES = sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "node_*.npz")))
 CONTRACT = 1e-3        # BASELINE.json north_star: relative fp32 on the final latent
-EXPECTED = 2e-4        # what fp32 round-off through a whole sampler run leaves room for
+EXPECTED = 5e-6        # fp32 round-off through a whole sampler run (measured on B200: <= 4.6e-7 over the 13 cases)
 _MEASURED = {}
 
 
@@ -39,10 +41,10 @@ def load_node_golden(name):
 
 
 def test_fixture_inventory():
-    assert len(NODE_CASES) >= 12
+    assert len(NODE_CASES) >= 13
     nodes = {load_node_golden(n)["meta"]["node"] for n in NODE_CASES}
     assert nodes == {"LanPaint_KSampler", "LanPaint_KSamplerAdvanced", "LanPaint_SamplerCustom",
-                     "LanPaint_SamplerCustomAdvanced"}
+                     "LanPaint_SamplerCustomAdvanced", "outer_sample_av_pack"}
 
 
 @pytest.mark.parametrize("name", NODE_CASES)
