@@ -98,6 +98,47 @@ def test_node_matches_reference_node_layer(name, cuda_device):
     assert err <= EXPECTED, f"{name}: {err:.3e} is inside the 1e-3 contract but above fp32 round-off"
 
 
+@pytest.mark.parametrize("name", NODE_CASES)
+def test_engine_seam_under_the_reference_node_layer(name, cuda_device, monkeypatch):
+    """INTEGRATION.md seam 2, literally: the REFERENCE's own node layer (oracle/_ref bytecode of nodes.py: its patch
+    seam, its per-sigma wrapper with device-resident sigma / current_times and a full-shape fp32 latent_mask) with the
+    one-line engine swap `LanPaint = lanpaint_b200.engine.LanPaint` (nodes.py:18), on the GPU, against the outputs the
+    same node layer produced with the reference's engine."""
+    import contextlib
+    import io
+    from oracle import build_ref
+    ref_nodes = build_ref.load_nodes()
+    if ref_nodes is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference: `make -C oracle`)")
+    from lanpaint_b200.engine import LanPaint, NoiseTape
+    monkeypatch.setattr(ref_nodes, "LanPaint", LanPaint)
+    g = load_node_golden(name)
+    c = g["meta"]
+    dev = cuda_device
+    calls = {"n": 0}
+
+    def net(x, sigma, cond):
+        calls["n"] += 1
+        return denoiser(x, sigma, cond)
+
+    patcher = build_patcher(c, device=dev, net=net)
+    tape = NoiseTape([torch.from_numpy(t.astype(np.float32)) for t in g["tape"]])
+    patcher.model_options["lanpaint_b200"] = {"rng": tape}
+    latent = {"samples": torch.from_numpy(g["samples"])}
+    if "noise_mask" in g:
+        latent["noise_mask"] = torch.from_numpy(g["noise_mask"].astype(np.float32))
+    noise_image = torch.from_numpy(g["noise_image"]) if "noise_image" in g else None
+    comfy_sample = sys.modules["comfy.sample"]
+    with mock.patch.object(comfy_sample, "prepare_noise", lambda *a, **k: noise_image.clone()), \
+            mock.patch.object(torch, "randn_like", lambda like, **kw: tape.next(like)), \
+            contextlib.redirect_stdout(io.StringIO()):
+        outs = call_node(ref_nodes, c, patcher, latent, noise_image)
+    assert tape.pos == c["n_draws"] and calls["n"] == c["network_calls"]
+    err = max_rel(outs[0]["samples"], torch.from_numpy(g["out"]))
+    _MEASURED[name + ":reference-nodes+b200-engine"] = err
+    assert err <= EXPECTED, err
+
+
 def test_report_measured_errors():
     """Writes the measured deviations where a gpurun call brings them back (gpurun_out/)."""
     if not _MEASURED:
