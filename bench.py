@@ -502,279 +502,290 @@ def run_b200(args):
                   "in, LATENT dict of host tensors out (every call: ComfyUI's CPU prepare_noise, H2D, sampler loop, D2H)"}
     launches = (wl_main.stats()["graph_nodes_per_job"] or 0) * K * J * world
 
-    # ---- the other randn stream, same measurement (fewer steps) ------------------------------------------------
-    variants = {}
-    if not args.quick:
-        v, _ = measure(spec_main, other_rng, max(2, K // 4), 1, J)
-        variants[other_rng] = {"value": v["value"], "ms_per_job_device": v["ms_per_job_device"],
-                               "e2e": {"value": v["e2e_value"], "unit": "sub-steps/s", "ms_per_job_wall": v["ms_per_job_wall"],
-                                       "api": f"lanpaint_b200.comfy_nodes.LanPaint_KSampler.sample, rng={other_rng}"},
-                               "jobs": v["jobs"], "launch": v["launch"]}
+    # ---- secondary records: an exception in any of them is reported in the line, never in place of it ----------
+    variants, serving, roofs, configs, other_sampler, real_network, frame_shard, cpu = {}, None, {}, None, None, None, None, None
+    peak, peak_src = peaks()
+    roof = {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
+            "peak_source": peak_src, "note": "kernel timer not run"}
+    secondary_error = None
+    try:
+        # ---- rooflines: the steady fused sub-step of each stream (and with bf16 heads), live CUDA-event timing ------
+        peak, peak_src = peaks()
+        roofs = {}
+        if args.kernel_timer:
+            g = torch.Generator().manual_seed(90 + rank)
+            y = torch.randn((R,) + SHAPE, generator=g).to(dev)
+            known = (torch.rand((R, 1) + SHAPE[1:], generator=g) < 0.5).to(dev)
+            pm = pack_mask(known, y)
+            n_el = R * SHAPE[0] * SHAPE[1] * SHAPE[2]
+            kernels = {"torch": ("lp::substep_torch_tma_kernel<float, first=0, next=1> (steady fused sub-step, torch.randn stream, "
+                                 "producer warp + 4 plane slots of cp.async.bulk)", torch.float32),
+                       "philox": ("lp::substep_tma_kernel<float, first=0, next=1, merge=1> (steady fused sub-step, philox stream, "
+                                  "TMA-staged persistent)", torch.float32),
+                       "torch_bf16_heads": ("lp::substep_torch_tma_kernel<bf16, first=0, next=1>", torch.bfloat16),
+                       "philox_bf16_heads": ("lp::substep_tma_kernel<bf16, first=0, next=1, merge=1>", torch.bfloat16)}
+            for key, (kname, hdtype) in kernels.items():
+                rng = key.split("_")[0]
+                eng = LanPaint(SynthDenoiser(VESampling(), dtype=hdtype), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0,
+                               StepSize=0.2, MinStepFrac=1.0, rng=rng, batched_replace="per_sample")
+                algo = algo_bytes_per_elem(SHAPE[0], 4 if hdtype == torch.float32 else 2) * n_el
+                burst = sorted(time_steady_substep(eng, y, pm, sigma=2.0, launches=53, repeats=20, rotate=3))
+                avg = sum(burst) / len(burst)
+                rec = {"bound": "hbm", "achieved": algo / (avg * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": algo / (avg * 1e-6) / 1e9 / peak, "traffic": None, "kernel": kname, "peak_source": peak_src,
+                       "algorithmic_bytes_per_launch": algo, "avg_us": avg, "median_us": burst[len(burst) // 2],
+                       "min_us": burst[0], "launches_timed": 53 * len(burst)}
+                if key in ("torch", "philox"):
+                    warm = sorted(time_steady_substep(eng, y, pm, sigma=2.0, launches=53, repeats=10, rotate=1))
+                    rec["same_buffers_us"] = sum(warm) / len(warm)   # one operand set re-used: the L2 keeps part of it
+                tr = os.path.join(ROOT, "profiles", "traffic.json")
+                if os.path.exists(tr):
+                    rec["traffic"] = json.load(open(tr)).get(f"{key}_{R}", json.load(open(tr)).get(str(R)) if key == "philox" else None)
+                roofs[key] = rec
+            roofs[args.rng]["timing"] = ("53 back-to-back launches of the steady fused sub-step between two CUDA events on the "
+                                         "launching stream, x20, cycling 3 independent job-shaped operand sets so every launch's "
+                                         "operands were evicted from L2 by the two launches before it (true HBM streaming)")
+            roofs[args.rng]["substep_share_of_step"] = 53 * roofs[args.rng]["avg_us"] * 1e-3 / main["ms_per_job_device"]
+            if rank == 0:
+                # context for the fractions: the same copy probe MEASURED_PEAKS.json was produced with, on THIS box
+                try:
+                    a_ = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+                    b_ = torch.empty_like(a_)
+                    best = float("inf")
+                    for _ in range(10):
+                        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        c0.record()
+                        b_.copy_(a_)
+                        c1.record()
+                        c1.synchronize()
+                        best = min(best, c0.elapsed_time(c1))
+                    roofs[args.rng]["copy_gbs_this_box"] = 2 * a_.numel() * 2 / (best * 1e-3) / 1e9
+                    del a_, b_
+                except Exception:
+                    pass
+            torch.cuda.empty_cache()
+        roof = roofs.get(args.rng) or {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                                       "traffic": None, "peak_source": peak_src}
 
-    # ---- serving path: runner.GraphedJob (host-owned sampler loop, whole job = one graph), same guider ---------
-    serving = None
-    if not args.quick:
-        serving = {}
-        sched = HostSchedule(karras_sigmas(N_OUTER), R, N_INNER)
-        g = torch.Generator().manual_seed(50 + rank)
-        y = torch.randn((R,) + SHAPE, generator=g).to(dev)
-        noise = torch.randn((R,) + SHAPE, generator=g).to(dev)
-        known = (torch.rand((R, 1) + SHAPE[1:], generator=g) < 0.5).to(dev)
-        pm = pack_mask(known, y)
-        for rng in (args.rng, other_rng):
-            net = SynthCondNet(tuple(weights.tolist()))
-            eng = LanPaint(DirectGuider(net, VESampling(), 5.0, 5.0), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0,
-                           StepSize=0.2, MinStepFrac=1.0, rng=rng, batched_replace="per_sample")
+        # ---- the other randn stream, same measurement (fewer steps) ------------------------------------------------
+        variants = {}
+        if not args.quick:
+            v, _ = measure(spec_main, other_rng, max(2, K // 4), 1, J)
+            variants[other_rng] = {"value": v["value"], "ms_per_job_device": v["ms_per_job_device"],
+                                   "e2e": {"value": v["e2e_value"], "unit": "sub-steps/s", "ms_per_job_wall": v["ms_per_job_wall"],
+                                           "api": f"lanpaint_b200.comfy_nodes.LanPaint_KSampler.sample, rng={other_rng}"},
+                                   "jobs": v["jobs"], "launch": v["launch"]}
+
+        # ---- serving path: runner.GraphedJob (host-owned sampler loop, whole job = one graph), same guider ---------
+        serving = None
+        if not args.quick:
+            serving = {}
+            sched = HostSchedule(karras_sigmas(N_OUTER), R, N_INNER)
+            g = torch.Generator().manual_seed(50 + rank)
+            y = torch.randn((R,) + SHAPE, generator=g).to(dev)
+            noise = torch.randn((R,) + SHAPE, generator=g).to(dev)
+            known = (torch.rand((R, 1) + SHAPE[1:], generator=g) < 0.5).to(dev)
+            pm = pack_mask(known, y)
+            for rng in (args.rng, other_rng):
+                net = SynthCondNet(tuple(weights.tolist()))
+                eng = LanPaint(DirectGuider(net, VESampling(), 5.0, 5.0), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0,
+                               StepSize=0.2, MinStepFrac=1.0, rng=rng, batched_replace="per_sample")
+                job = GraphedJob(eng, sched, (R,) + SHAPE, dev)
+                for _ in range(3):
+                    job.run(y, noise, pm)
+                group.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_jobs = max(20, K)
+                e0.record()
+                for _ in range(n_jobs):
+                    job.run(y, noise, pm)
+                e1.record()
+                group.barrier()
+                ms = group.max_over_ranks(e0.elapsed_time(e1))
+                serving[rng] = {"value": world * R * sched.substeps * n_jobs / (ms * 1e-3), "ms_per_job": ms / n_jobs,
+                                "graph_nodes_per_job": job.launches + 2 * job.model_calls,
+                                "api": "lanpaint_b200.runner.GraphedJob.run, device-resident inputs, one CUDA graph per job"}
+                del job, eng
+            # round 1's headline configuration for continuity: two-head synthetic network (ONE kernel per guider evaluation
+            # instead of a cond and an uncond one), philox stream, whole-job graph
+            eng = LanPaint(SynthDenoiser(VESampling()), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0, StepSize=0.2,
+                           MinStepFrac=1.0, rng="philox", batched_replace="per_sample")
             job = GraphedJob(eng, sched, (R,) + SHAPE, dev)
             for _ in range(3):
                 job.run(y, noise, pm)
             group.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n_jobs = max(20, K)
             e0.record()
             for _ in range(n_jobs):
                 job.run(y, noise, pm)
             e1.record()
             group.barrier()
             ms = group.max_over_ranks(e0.elapsed_time(e1))
-            serving[rng] = {"value": world * R * sched.substeps * n_jobs / (ms * 1e-3), "ms_per_job": ms / n_jobs,
-                            "graph_nodes_per_job": job.launches + 2 * job.model_calls,
-                            "api": "lanpaint_b200.runner.GraphedJob.run, device-resident inputs, one CUDA graph per job"}
+            serving["round1_headline_config"] = {"value": world * R * sched.substeps * n_jobs / (ms * 1e-3), "ms_per_job": ms / n_jobs,
+                                                 "graph_nodes_per_job": job.launches + job.model_calls,
+                                                 "what": "two-head synthetic network (73 network kernels per request instead of "
+                                                         "146), rng=philox, runner.GraphedJob: the configuration of BENCH_r01.value"}
             del job, eng
-        # round 1's headline configuration for continuity: two-head synthetic network (ONE kernel per guider evaluation
-        # instead of a cond and an uncond one), philox stream, whole-job graph
-        eng = LanPaint(SynthDenoiser(VESampling()), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0, StepSize=0.2,
-                       MinStepFrac=1.0, rng="philox", batched_replace="per_sample")
-        job = GraphedJob(eng, sched, (R,) + SHAPE, dev)
-        for _ in range(3):
-            job.run(y, noise, pm)
-        group.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n_jobs):
-            job.run(y, noise, pm)
-        e1.record()
-        group.barrier()
-        ms = group.max_over_ranks(e0.elapsed_time(e1))
-        serving["round1_headline_config"] = {"value": world * R * sched.substeps * n_jobs / (ms * 1e-3), "ms_per_job": ms / n_jobs,
-                                             "graph_nodes_per_job": job.launches + job.model_calls,
-                                             "what": "two-head synthetic network (73 network kernels per request instead of "
-                                                     "146), rng=philox, runner.GraphedJob: the configuration of BENCH_r01.value"}
-        del job, eng
-        if world == 1:   # batch-size sweep of that configuration (R = 256: every byte from HBM; small R: launch-bound)
-            sweep = []
-            for r in (1, 8, 32, 64, 256):
-                s_r = HostSchedule(karras_sigmas(N_OUTER), r, N_INNER)
-                g_r = torch.Generator().manual_seed(5)
-                y_r = torch.randn((r,) + SHAPE, generator=g_r).to(dev)
-                n_r = torch.randn((r,) + SHAPE, generator=g_r).to(dev)
-                p_r = pack_mask((torch.rand((r, 1) + SHAPE[1:], generator=g_r) < 0.5).to(dev), y_r)
-                e_r = LanPaint(SynthDenoiser(VESampling()), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0, StepSize=0.2,
-                               MinStepFrac=1.0, rng="philox", batched_replace="per_sample")
-                j_r = GraphedJob(e_r, s_r, (r,) + SHAPE, dev)
-                for _ in range(3):
-                    j_r.run(y_r, n_r, p_r)
-                torch.cuda.synchronize()
-                reps = 40 if r <= 64 else 12
-                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a0.record()
-                for _ in range(reps):
-                    j_r.run(y_r, n_r, p_r)
-                a1.record()
-                torch.cuda.synchronize()
-                t_r = a0.elapsed_time(a1) / reps
-                sweep.append({"requests_per_gpu": r, "ms_per_job": t_r, "value": r * s_r.substeps / (t_r * 1e-3),
-                              "us_per_graph_node": 1e3 * t_r / (j_r.launches + j_r.model_calls)})
-                del j_r, e_r, y_r, n_r, p_r
+            if world == 1:   # batch-size sweep of that configuration (R = 256: every byte from HBM; small R: launch-bound)
+                sweep = []
+                for r in (1, 8, 32, 64, 256):
+                    s_r = HostSchedule(karras_sigmas(N_OUTER), r, N_INNER)
+                    g_r = torch.Generator().manual_seed(5)
+                    y_r = torch.randn((r,) + SHAPE, generator=g_r).to(dev)
+                    n_r = torch.randn((r,) + SHAPE, generator=g_r).to(dev)
+                    p_r = pack_mask((torch.rand((r, 1) + SHAPE[1:], generator=g_r) < 0.5).to(dev), y_r)
+                    e_r = LanPaint(SynthDenoiser(VESampling()), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0, StepSize=0.2,
+                                   MinStepFrac=1.0, rng="philox", batched_replace="per_sample")
+                    j_r = GraphedJob(e_r, s_r, (r,) + SHAPE, dev)
+                    for _ in range(3):
+                        j_r.run(y_r, n_r, p_r)
+                    torch.cuda.synchronize()
+                    reps = 40 if r <= 64 else 12
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    for _ in range(reps):
+                        j_r.run(y_r, n_r, p_r)
+                    a1.record()
+                    torch.cuda.synchronize()
+                    t_r = a0.elapsed_time(a1) / reps
+                    sweep.append({"requests_per_gpu": r, "ms_per_job": t_r, "value": r * s_r.substeps / (t_r * 1e-3),
+                                  "us_per_graph_node": 1e3 * t_r / (j_r.launches + j_r.model_calls)})
+                    del j_r, e_r, y_r, n_r, p_r
+                    torch.cuda.empty_cache()
+                serving["round1_headline_config"]["sweep"] = sweep
+            ref_ms = serving[args.rng]["ms_per_job"]
+            serving["node_api_over_graphed_job"] = main["ms_per_job_device"] / ref_ms
+            # host tensors in, host result out through the same object, two batches in flight, uint8 mask, noise drawn on
+            # the device (serving hosts do not need ComfyUI's CPU noise image): round 1's e2e, with less PCIe traffic
+            lanes = []
+            for lane in range(2):
+                gl = torch.Generator().manual_seed(70 + rank + 17 * lane)
+                hy = torch.randn((R,) + SHAPE, generator=gl).pin_memory()
+                hm = (torch.rand((R, 1) + SHAPE[1:], generator=gl) < 0.5).to(torch.uint8).pin_memory()
+                net = SynthCondNet(tuple(weights.tolist()))
+                eng = LanPaint(DirectGuider(net, VESampling(), 5.0, 5.0), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0,
+                               StepSize=0.2, MinStepFrac=1.0, rng=args.rng, batched_replace="per_sample")
+                lanes.append({"y": hy, "m": hm, "out": torch.empty((R,) + SHAPE).pin_memory(),
+                              "stream": torch.cuda.Stream(device=dev), "job": GraphedJob(eng, sched, (R,) + SHAPE, dev)})
+
+            def submit(ln):
+                with torch.cuda.stream(ln["stream"]):
+                    ln["job"].run(ln["y"], None, ln["m"].to(dev, non_blocking=True), x_out=ln["out"])
+
+            def run_lanes(n):
+                for i in range(n):
+                    ln = lanes[i % 2]
+                    ln["stream"].synchronize()      # the previous result of this lane is on the host: the user has it
+                    submit(ln)
+                for ln in lanes:
+                    ln["stream"].synchronize()
+            run_lanes(6)
+            group.barrier()
+            n_jobs = max(20, K)
+            t0 = time.perf_counter()
+            run_lanes(n_jobs)
+            group.barrier()
+            dt = group.max_over_ranks(time.perf_counter() - t0)
+            bi = lanes[0]["y"].numel() * 4 + lanes[0]["m"].numel()
+            bo = lanes[0]["out"].numel() * 4
+            serving["e2e"] = {"value": world * R * sched.substeps * n_jobs / dt, "unit": "sub-steps/s",
+                              "h2d_bytes_per_job": bi, "d2h_bytes_per_job": bo, "jobs": n_jobs, "in_flight": 2,
+                              "pcie_gbs": {"h2d": bi * n_jobs / dt / 1e9, "d2h": bo * n_jobs / dt / 1e9},
+                              "api": f"lanpaint_b200.runner.GraphedJob.run(latent pinned host, noise=None (drawn on the device), "
+                                     f"uint8 mask pinned host) -> pinned host result, rng={args.rng}"}
+            del lanes
+
+        # ---- the literal BASELINE configurations, each through the node API ------------------------------------------
+        configs = None
+        specs = [Spec("cfg2_sdxl_batch1_N5", 1, SHAPE, note="BASELINE configs[1]"),
+                 Spec("sdxl_batch8_N5", 8, SHAPE, note="north_star target shape"),
+                 Spec("cfg3_sdxl_4_per_gpu_N10", 4, SHAPE, n_inner=10, note="BASELINE configs[2]: batch 32 = 4 per GPU x 8"),
+                 Spec("cfg4_flux_16x128x128_flow_simple20", 1, (16, 128, 128), flow=True, shift=1.0, scheduler="simple",
+                      cfg=1.0 + 2.5, note="BASELINE configs[3] at the ComfyUI boundary (patchify is inside the DiT)"),
+                 Spec("cfg5_wan_16x21x80x45_flow_simple20_shift3", 1, (16, 21, 80, 45), flow=True, shift=3.0, scheduler="simple",
+                      note="BASELINE configs[4], 81 frames -> 21 latent frames, one GPU holds the sample (see --frame-shard)")]
+        if args.configs and not args.quick:
+            configs = []
+            for sp in specs:
+                if world > 1 and not sp.name.startswith("cfg3"):
+                    continue           # SCALE carries cfg3 (32 requests over 8 GPUs); the rest are single-GPU records
+                recs = {}
+                for rng in (args.rng, other_rng):
+                    r_, wl = measure(sp, rng, 1, 0, 12 if sp.batch <= 8 else 6, seed=rank + 3)
+                    recs[rng] = r_
+                r0 = recs[args.rng]
+                c = {"name": sp.name, "note": sp.note, "latent_shape": list(sp.shape), "think_steps": sp.n_inner,
+                     "schedule": f"{sp.scheduler}-{sp.steps}" + (f" shift {sp.shift}" if sp.flow else ""),
+                     "substeps": r0["substeps_per_request"], "guider_calls": r0["guider_calls_per_request"],
+                     "n_gpus": world, "api": "comfy_nodes.LanPaint_KSampler.sample"}
+                for rng, r_ in recs.items():
+                    nodes = r_["launch"]["graph_nodes_per_job"]
+                    algo = algo_bytes_per_elem(sp.latent[0]) * sp.n_el * r_["substeps_per_request"]
+                    c[rng] = {"value": r_["value"], "ms_per_job_device": r_["ms_per_job_device"], "e2e_value": r_["e2e_value"],
+                              "ms_per_job_wall": r_["ms_per_job_wall"], "launch_mode": r_["launch"]["mode"],
+                              "graph_nodes_per_job": nodes,
+                              "us_per_graph_node": 1e3 * r_["ms_per_job_device"] / nodes if nodes else None,
+                              "substep_algorithmic_gbs": algo / (r_["ms_per_job_device"] * 1e-3) / 1e9,
+                              "regime": "latency / L2 (working set %.1f MB per launch)" % (5.25 * 4 * sp.n_el / 1e6)}
+                if rank == 0 and world == 1:
+                    c["reference_eager_on_this_gpu"] = eager_reference_on_gpu(sp, dev)
+                    if c["reference_eager_on_this_gpu"].get("ms_per_job"):
+                        c["speedup_vs_reference_on_this_gpu"] = (c["reference_eager_on_this_gpu"]["ms_per_job"] /
+                                                                c[args.rng]["ms_per_job_device"])
+                configs.append(c)
                 torch.cuda.empty_cache()
-            serving["round1_headline_config"]["sweep"] = sweep
-        ref_ms = serving[args.rng]["ms_per_job"]
-        serving["node_api_over_graphed_job"] = main["ms_per_job_device"] / ref_ms
-        # host tensors in, host result out through the same object, two batches in flight, uint8 mask, noise drawn on
-        # the device (serving hosts do not need ComfyUI's CPU noise image): round 1's e2e, with less PCIe traffic
-        lanes = []
-        for lane in range(2):
-            gl = torch.Generator().manual_seed(70 + rank + 17 * lane)
-            hy = torch.randn((R,) + SHAPE, generator=gl).pin_memory()
-            hm = (torch.rand((R, 1) + SHAPE[1:], generator=gl) < 0.5).to(torch.uint8).pin_memory()
-            net = SynthCondNet(tuple(weights.tolist()))
-            eng = LanPaint(DirectGuider(net, VESampling(), 5.0, 5.0), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0,
-                           StepSize=0.2, MinStepFrac=1.0, rng=args.rng, batched_replace="per_sample")
-            lanes.append({"y": hy, "m": hm, "out": torch.empty((R,) + SHAPE).pin_memory(),
-                          "stream": torch.cuda.Stream(device=dev), "job": GraphedJob(eng, sched, (R,) + SHAPE, dev)})
 
-        def submit(ln):
-            with torch.cuda.stream(ln["stream"]):
-                ln["job"].run(ln["y"], None, ln["m"].to(dev, non_blocking=True), x_out=ln["out"])
-
-        def run_lanes(n):
-            for i in range(n):
-                ln = lanes[i % 2]
-                ln["stream"].synchronize()      # the previous result of this lane is on the host: the user has it
-                submit(ln)
-            for ln in lanes:
-                ln["stream"].synchronize()
-        run_lanes(6)
-        group.barrier()
-        n_jobs = max(20, K)
-        t0 = time.perf_counter()
-        run_lanes(n_jobs)
-        group.barrier()
-        dt = group.max_over_ranks(time.perf_counter() - t0)
-        bi = lanes[0]["y"].numel() * 4 + lanes[0]["m"].numel()
-        bo = lanes[0]["out"].numel() * 4
-        serving["e2e"] = {"value": world * R * sched.substeps * n_jobs / dt, "unit": "sub-steps/s",
-                          "h2d_bytes_per_job": bi, "d2h_bytes_per_job": bo, "jobs": n_jobs, "in_flight": 2,
-                          "pcie_gbs": {"h2d": bi * n_jobs / dt / 1e9, "d2h": bo * n_jobs / dt / 1e9},
-                          "api": f"lanpaint_b200.runner.GraphedJob.run(latent pinned host, noise=None (drawn on the device), "
-                                 f"uint8 mask pinned host) -> pinned host result, rng={args.rng}"}
-        del lanes
-
-    # ---- rooflines: the steady fused sub-step of each stream (and with bf16 heads), live CUDA-event timing ------
-    peak, peak_src = peaks()
-    roofs = {}
-    if args.kernel_timer:
-        g = torch.Generator().manual_seed(90 + rank)
-        y = torch.randn((R,) + SHAPE, generator=g).to(dev)
-        known = (torch.rand((R, 1) + SHAPE[1:], generator=g) < 0.5).to(dev)
-        pm = pack_mask(known, y)
-        n_el = R * SHAPE[0] * SHAPE[1] * SHAPE[2]
-        kernels = {"torch": ("lp::substep_torch_tma_kernel<float, first=0, next=1> (steady fused sub-step, torch.randn stream, "
-                             "producer warp + 4 plane slots of cp.async.bulk)", torch.float32),
-                   "philox": ("lp::substep_tma_kernel<float, first=0, next=1, merge=1> (steady fused sub-step, philox stream, "
-                              "TMA-staged persistent)", torch.float32),
-                   "torch_bf16_heads": ("lp::substep_torch_tma_kernel<bf16, first=0, next=1>", torch.bfloat16),
-                   "philox_bf16_heads": ("lp::substep_tma_kernel<bf16, first=0, next=1, merge=1>", torch.bfloat16)}
-        for key, (kname, hdtype) in kernels.items():
-            rng = key.split("_")[0]
-            eng = LanPaint(SynthDenoiser(VESampling(), dtype=hdtype), NSteps=N_INNER, Friction=15.0, Lambda=5.0, Beta=1.0,
-                           StepSize=0.2, MinStepFrac=1.0, rng=rng, batched_replace="per_sample")
-            algo = algo_bytes_per_elem(SHAPE[0], 4 if hdtype == torch.float32 else 2) * n_el
-            burst = sorted(time_steady_substep(eng, y, pm, sigma=2.0, launches=53, repeats=20, rotate=3))
-            avg = sum(burst) / len(burst)
-            rec = {"bound": "hbm", "achieved": algo / (avg * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
-                   "frac": algo / (avg * 1e-6) / 1e9 / peak, "traffic": None, "kernel": kname, "peak_source": peak_src,
-                   "algorithmic_bytes_per_launch": algo, "avg_us": avg, "median_us": burst[len(burst) // 2],
-                   "min_us": burst[0], "launches_timed": 53 * len(burst)}
-            if key in ("torch", "philox"):
-                warm = sorted(time_steady_substep(eng, y, pm, sigma=2.0, launches=53, repeats=10, rotate=1))
-                rec["same_buffers_us"] = sum(warm) / len(warm)   # one operand set re-used: the L2 keeps part of it
-            tr = os.path.join(ROOT, "profiles", "traffic.json")
-            if os.path.exists(tr):
-                rec["traffic"] = json.load(open(tr)).get(f"{key}_{R}", json.load(open(tr)).get(str(R)) if key == "philox" else None)
-            roofs[key] = rec
-        roofs[args.rng]["timing"] = ("53 back-to-back launches of the steady fused sub-step between two CUDA events on the "
-                                     "launching stream, x20, cycling 3 independent job-shaped operand sets so every launch's "
-                                     "operands were evicted from L2 by the two launches before it (true HBM streaming)")
-        roofs[args.rng]["substep_share_of_step"] = 53 * roofs[args.rng]["avg_us"] * 1e-3 / main["ms_per_job_device"]
-        if rank == 0:
-            # context for the fractions: the same copy probe MEASURED_PEAKS.json was produced with, on THIS box
-            try:
-                a_ = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
-                b_ = torch.empty_like(a_)
-                best = float("inf")
-                for _ in range(10):
-                    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    c0.record()
-                    b_.copy_(a_)
-                    c1.record()
-                    c1.synchronize()
-                    best = min(best, c0.elapsed_time(c1))
-                roofs[args.rng]["copy_gbs_this_box"] = 2 * a_.numel() * 2 / (best * 1e-3) / 1e9
-                del a_, b_
-            except Exception:
-                pass
-        torch.cuda.empty_cache()
-    roof = roofs.get(args.rng) or {"bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
-                                   "traffic": None, "peak_source": peak_src}
-
-    # ---- the literal BASELINE configurations, each through the node API ------------------------------------------
-    configs = None
-    specs = [Spec("cfg2_sdxl_batch1_N5", 1, SHAPE, note="BASELINE configs[1]"),
-             Spec("sdxl_batch8_N5", 8, SHAPE, note="north_star target shape"),
-             Spec("cfg3_sdxl_4_per_gpu_N10", 4, SHAPE, n_inner=10, note="BASELINE configs[2]: batch 32 = 4 per GPU x 8"),
-             Spec("cfg4_flux_16x128x128_flow_simple20", 1, (16, 128, 128), flow=True, shift=1.0, scheduler="simple",
-                  cfg=1.0 + 2.5, note="BASELINE configs[3] at the ComfyUI boundary (patchify is inside the DiT)"),
-             Spec("cfg5_wan_16x21x80x45_flow_simple20_shift3", 1, (16, 21, 80, 45), flow=True, shift=3.0, scheduler="simple",
-                  note="BASELINE configs[4], 81 frames -> 21 latent frames, one GPU holds the sample (see --frame-shard)")]
-    if args.configs and not args.quick:
-        configs = []
-        for sp in specs:
-            if world > 1 and not sp.name.startswith("cfg3"):
-                continue           # SCALE carries cfg3 (32 requests over 8 GPUs); the rest are single-GPU records
-            recs = {}
-            for rng in (args.rng, other_rng):
-                r_, wl = measure(sp, rng, 1, 0, 12 if sp.batch <= 8 else 6, seed=rank + 3)
-                recs[rng] = r_
-            r0 = recs[args.rng]
-            c = {"name": sp.name, "note": sp.note, "latent_shape": list(sp.shape), "think_steps": sp.n_inner,
-                 "schedule": f"{sp.scheduler}-{sp.steps}" + (f" shift {sp.shift}" if sp.flow else ""),
-                 "substeps": r0["substeps_per_request"], "guider_calls": r0["guider_calls_per_request"],
-                 "n_gpus": world, "api": "comfy_nodes.LanPaint_KSampler.sample"}
-            for rng, r_ in recs.items():
-                nodes = r_["launch"]["graph_nodes_per_job"]
-                algo = algo_bytes_per_elem(sp.latent[0]) * sp.n_el * r_["substeps_per_request"]
-                c[rng] = {"value": r_["value"], "ms_per_job_device": r_["ms_per_job_device"], "e2e_value": r_["e2e_value"],
-                          "ms_per_job_wall": r_["ms_per_job_wall"], "launch_mode": r_["launch"]["mode"],
-                          "graph_nodes_per_job": nodes,
-                          "us_per_graph_node": 1e3 * r_["ms_per_job_device"] / nodes if nodes else None,
-                          "substep_algorithmic_gbs": algo / (r_["ms_per_job_device"] * 1e-3) / 1e9,
-                          "regime": "latency / L2 (working set %.1f MB per launch)" % (5.25 * 4 * sp.n_el / 1e6)}
-            if rank == 0 and world == 1:
-                c["reference_eager_on_this_gpu"] = eager_reference_on_gpu(sp, dev)
-                if c["reference_eager_on_this_gpu"].get("ms_per_job"):
-                    c["speedup_vs_reference_on_this_gpu"] = (c["reference_eager_on_this_gpu"]["ms_per_job"] /
-                                                            c[args.rng]["ms_per_job_device"])
-            configs.append(c)
+        # ---- another sampler through the same node: k-diffusion's own loop captured as one graph ---------------------
+        other_sampler = None
+        if args.configs and not args.quick and world == 1:
+            rec, wl = measure(Spec("sdxl_batch_heun", R, SHAPE, sampler="heun"), args.rng, 1, 0, 8, seed=rank + 7)
+            other_sampler = {"sampler": "heun", "requests_per_gpu": R, "value": rec["value"],
+                             "ms_per_job_device": rec["ms_per_job_device"], "e2e_value": rec["e2e_value"],
+                             "substeps_per_request": rec["substeps_per_request"],
+                             "guider_calls_per_request": rec["guider_calls_per_request"], "launch": rec["launch"],
+                             "note": "heun evaluates the wrapper twice per step; its whole loop (k-diffusion's Python) is captured "
+                                     "into one CUDA graph after an eager first job recorded the sigma sequence"}
+            del wl
             torch.cuda.empty_cache()
 
-    # ---- another sampler through the same node: k-diffusion's own loop captured as one graph ---------------------
-    other_sampler = None
-    if args.configs and not args.quick and world == 1:
-        rec, wl = measure(Spec("sdxl_batch_heun", R, SHAPE, sampler="heun"), args.rng, 1, 0, 8, seed=rank + 7)
-        other_sampler = {"sampler": "heun", "requests_per_gpu": R, "value": rec["value"],
-                         "ms_per_job_device": rec["ms_per_job_device"], "e2e_value": rec["e2e_value"],
-                         "substeps_per_request": rec["substeps_per_request"],
-                         "guider_calls_per_request": rec["guider_calls_per_request"], "launch": rec["launch"],
-                         "note": "heun evaluates the wrapper twice per step; its whole loop (k-diffusion's Python) is captured "
-                                 "into one CUDA graph after an eager first job recorded the sigma sequence"}
-        del wl
-        torch.cuda.empty_cache()
+        # ---- cfg4 with a real PyTorch network captured in the graphs -------------------------------------------------
+        real_network = None
+        if args.real_network and not args.quick and world == 1:
+            try:
+                real_network = run_real_network(dev, args)
+            except Exception as e:   # an informational record never breaks the bench line
+                real_network = {"error": f"{type(e).__name__}: {e}"}
 
-    # ---- cfg4 with a real PyTorch network captured in the graphs -------------------------------------------------
-    real_network = None
-    if args.real_network and not args.quick and world == 1:
-        try:
-            real_network = run_real_network(dev, args)
-        except Exception as e:   # an informational record never breaks the bench line
-            real_network = {"error": f"{type(e).__name__}: {e}"}
+        # ---- cfg5 frame-sharded synthetic run: one sample's frames split over the ranks ------------------------------
+        frame_shard = None
+        if args.frame_shard and not args.quick:
+            frame_shard = run_frame_shard(group, dev, args)
 
-    # ---- cfg5 frame-sharded synthetic run: one sample's frames split over the ranks ------------------------------
-    frame_shard = None
-    if args.frame_shard and not args.quick:
-        frame_shard = run_frame_shard(group, dev, args)
+        # ---- CPU baseline: the reference on the host cores, bounded sample (rank 0, N=1 only) ----
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu:
+            import warnings
+            warnings.filterwarnings("ignore")
+            host_cores = os.cpu_count() or 1
+            kind = reference_engine_kind()
+            ref_nodes = reference_nodes() if kind == "reference" else None
+            cores = calibrate_threads(args.ref_requests)
+            cpu_job(2, 2, cores)  # warm
+            if ref_nodes is not None:
+                dt, u = cpu_node_job(ref_nodes, args.ref_requests, cores)
+            else:
+                dt, u = cpu_job(args.ref_requests, N_OUTER, cores)
+            cpu = {"value": u / dt, "unit": "sub-steps/s", "cores": cores, "kind": kind,
+                   "same_reference_math_on_this_gpu": eager_reference_on_gpu(Spec("sdxl_batch8", args.ref_requests, SHAPE), dev),
+                   "sample": f"{args.ref_requests} of {R} requests, full karras-20 x N=5 schedule, {dt:.1f} s of CPU work; "
+                             f"{cores} torch threads (fastest of a probe over 1..{host_cores} host cores); "
+                             + (REFERENCE_API if ref_nodes is not None else
+                                "engine = the reference's own LanPaint.__call__ (oracle/_ref bytecode)" if kind == "reference"
+                                else "oracle port")}
 
-    # ---- CPU baseline: the reference on the host cores, bounded sample (rank 0, N=1 only) ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        import warnings
-        warnings.filterwarnings("ignore")
-        host_cores = os.cpu_count() or 1
-        kind = reference_engine_kind()
-        ref_nodes = reference_nodes() if kind == "reference" else None
-        cores = calibrate_threads(args.ref_requests)
-        cpu_job(2, 2, cores)  # warm
-        if ref_nodes is not None:
-            dt, u = cpu_node_job(ref_nodes, args.ref_requests, cores)
-        else:
-            dt, u = cpu_job(args.ref_requests, N_OUTER, cores)
-        cpu = {"value": u / dt, "unit": "sub-steps/s", "cores": cores, "kind": kind,
-               "same_reference_math_on_this_gpu": eager_reference_on_gpu(Spec("sdxl_batch8", args.ref_requests, SHAPE), dev),
-               "sample": f"{args.ref_requests} of {R} requests, full karras-20 x N=5 schedule, {dt:.1f} s of CPU work; "
-                         f"{cores} torch threads (fastest of a probe over 1..{host_cores} host cores); "
-                         + (REFERENCE_API if ref_nodes is not None else
-                            "engine = the reference's own LanPaint.__call__ (oracle/_ref bytecode)" if kind == "reference"
-                            else "oracle port")}
+    except Exception as e:
+        import traceback
+        secondary_error = f"{type(e).__name__}: {e} @ " + traceback.format_exc().strip().splitlines()[-3].strip()
 
     clocks.stop()
     if rank == 0:
@@ -791,7 +802,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfg, "roofline": roof, "rooflines": roofs, "cpu_baseline": cpu, "e2e": e2e,
             "variants": variants, "serving": serving, "frame_shard": frame_shard, "other_sampler": other_sampler,
-            "real_network": real_network,
+            "real_network": real_network, "secondary_error": secondary_error,
             "gpu_launches": launches, "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)
