@@ -633,6 +633,28 @@ def _weights_fingerprint(model_wrap):
     return id(net)
 
 
+def _cond_fingerprint(c, depth: int = 0):
+    """Identity of a CONDITIONING value as a captured graph sees it.  ComfyUI's CFGGuider.set_conds runs
+    `convert_cond` on every call: a NEW list of NEW dicts (each with a fresh `uuid`) around the SAME tensors -- the
+    text-encoder outputs ComfyUI's node cache keeps alive while the prompt is unchanged.  So containers are compared
+    structurally, tensors and other leaves by object identity (the cache entry pins them, an id cannot be recycled),
+    thin wrapper objects (comfy.conds.CONDRegular & co.: one `.cond` attribute) by what they wrap, `uuid` not at all."""
+    if isinstance(c, (str, int, float, bool, type(None))):
+        return c
+    if depth < 5:
+        if isinstance(c, dict):
+            return tuple((str(k), _cond_fingerprint(v, depth + 1)) for k, v in sorted(c.items(), key=lambda kv: str(kv[0]))
+                         if k != "uuid")
+        if isinstance(c, (list, tuple)):
+            return tuple(_cond_fingerprint(v, depth + 1) for v in c)
+        inner = getattr(c, "cond", None)
+        if inner is not None and not isinstance(c, torch.Tensor):
+            return (type(c).__name__, _cond_fingerprint(inner, depth + 1))
+    if isinstance(c, torch.Tensor):
+        return ("tensor", id(c), tuple(c.shape), str(c.dtype), str(c.device))
+    return ("object", id(c))
+
+
 class _EngineEntry:
     __slots__ = ("engine", "job", "runs", "graph_failed", "last_mode", "weights", "keep", "pinned", "eager_events",
                  "trace", "sampler_job", "sg_retries")
@@ -666,7 +688,8 @@ class _EngineCache:
         conds = getattr(model_wrap, "original_conds", None) or getattr(model_wrap, "conds", {}) or {}
         pos, neg = conds.get("positive"), conds.get("negative")
         net_opts = {k: v for k, v in model_options.items() if k != "lanpaint_b200"}
-        key = (id(model_wrap.model_patcher), id(pos), id(neg), float(model_wrap.cfg), float(model_wrap.cfg_BIG),
+        key = (id(model_wrap.model_patcher), _cond_fingerprint(pos), _cond_fingerprint(neg), float(model_wrap.cfg),
+               float(model_wrap.cfg_BIG),
                str(x.device), tuple(x.shape), str(x.dtype), tuple(sigmas_host), tuple(sorted(hyper.items())),
                early_stop, bool(max_denoise), options_fingerprint(opts), options_fingerprint(net_opts),
                bool(has_callback))

@@ -67,6 +67,33 @@ def test_cache_key_distinguishes_what_a_graph_bakes_in():
     assert _lookup(cache, _guider(patcher, pos, neg), x, model_options={"lanpaint_b200": {"timing": True}}) is e
 
 
+def test_conditioning_is_keyed_by_what_it_wraps_not_by_the_per_call_containers():
+    """ComfyUI's CFGGuider.set_conds -> convert_cond builds a new list of new dicts (fresh uuid, new CONDCrossAttn
+    wrappers) around the same text-encoder tensors on every call: that must hit the same entry; another prompt
+    (other tensors), another strength or an extra cond entry must not."""
+    import uuid
+
+    class CONDCrossAttn:       # comfy.conds.*: a thin wrapper with one `.cond`
+        def __init__(self, cond):
+            self.cond = cond
+
+    def convert(cross, pooled, strength=1.0):
+        return [{"cross_attn": cross, "pooled_output": pooled, "strength": strength, "uuid": uuid.uuid4(),
+                 "model_conds": {"c_crossattn": CONDCrossAttn(cross)}}]
+    cache = N._EngineCache(capacity=32)
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(lambda x, s, c: x), "cpu")
+    x = torch.zeros(1, 4, 8, 8)
+    t_pos, t_neg = torch.zeros(1, 77, 16), torch.zeros(1, 77, 16)
+    p_pos, p_neg = torch.zeros(1, 8), torch.zeros(1, 8)
+    e = _lookup(cache, _guider(patcher, convert(t_pos, p_pos), convert(t_neg, p_neg)), x)
+    assert _lookup(cache, _guider(patcher, convert(t_pos, p_pos), convert(t_neg, p_neg)), x) is e
+    assert _lookup(cache, _guider(patcher, convert(torch.zeros(1, 77, 16), p_pos), convert(t_neg, p_neg)), x) is not e
+    assert _lookup(cache, _guider(patcher, convert(t_pos, p_pos, 0.8), convert(t_neg, p_neg)), x) is not e
+    assert _lookup(cache, _guider(patcher, convert(t_pos, p_pos) * 2, convert(t_neg, p_neg)), x) is not e
+    assert _lookup(cache, _guider(patcher, convert(t_pos, p_pos), convert(t_neg, p_neg)), x) is e
+    assert e.keep[2][0]["cross_attn"] is t_pos          # the entry pins what its ids name
+
+
 def test_entry_is_dropped_when_the_weights_move_and_when_the_cache_is_full():
     cache = N._EngineCache(capacity=2)
     net = torch.nn.Linear(4, 4)
