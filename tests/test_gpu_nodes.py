@@ -576,3 +576,28 @@ def test_flux_shaped_transformer_under_the_node_graphs(cuda_device):
     assert eng.model_calls == model.calls
     for o in outs:
         assert max_rel(o, want) <= 1e-4, max_rel(o, want)
+
+
+def test_result_reaches_the_host_through_pinned_memory(cuda_device):
+    """ComfyUI finishes a sample call with `samples.to(intermediate_device())`; the patched outer_sample has already
+    put the result in a pinned tensor of the caching host allocator (same bytes, a fraction of the time), so that
+    `.to` is a no-op.  `{"pinned_result": False}` leaves the copy to ComfyUI; results below 64 KiB are left alone."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    dev = cuda_device
+    g = torch.Generator().manual_seed(9)
+    y = torch.randn(2, 4, 64, 64, generator=g)                  # 128 KiB
+    noise_mask = (torch.rand(2, 1, 64, 64, generator=g) < 0.5).float()
+    pinned, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False}, steps=6, n=2)
+    plain, _ = _ksampler_run(N, dev, y, noise_mask, opts={"cuda_graph": False, "pinned_result": False}, steps=6, n=2)
+    assert pinned.device.type == "cpu" and pinned.is_pinned() and not plain.is_pinned()
+    assert torch.equal(pinned, plain)
+    small, _ = _ksampler_run(N, dev, y[:1, :, :16, :16].contiguous(), noise_mask[:1, :, :16, :16].contiguous(),
+                             opts={"cuda_graph": False}, steps=6, n=2)
+    assert small.device.type == "cpu" and not small.is_pinned()
+    # the helper itself: non-contiguous input, another dtype, a CPU tensor passes through
+    t = torch.randn(64, 1024, device=dev).t()
+    h = N._host_result(t)
+    assert h.is_pinned() and torch.equal(h, t.cpu()) and N._host_result(h) is h
+    hb = N._host_result(torch.ones(1 << 16, dtype=torch.bfloat16, device=dev))
+    assert hb.dtype == torch.bfloat16 and hb.is_pinned() and float(hb.float().sum()) == float(1 << 16)
