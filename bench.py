@@ -406,12 +406,24 @@ class NodeWorkload:
         return self.N.LAST_RUN["mode"]
 
     def prepare_noise_ms(self, reps=3):
-        best = float("inf")
+        """-> (ms of the noise image as THIS call draws it, ms of ComfyUI's own CPU prepare_noise, where it is drawn)."""
+        best_cpu = float("inf")
         for k in range(reps):
             t0 = time.perf_counter()
             self.minicomfy.prepare_noise(self.latent["samples"], 7 + k)
+            best_cpu = min(best_cpu, time.perf_counter() - t0)
+        dev = self.N._noise_device(self.patcher)
+        if dev is None:
+            return 1e3 * best_cpu, 1e3 * best_cpu, "cpu (ComfyUI's prepare_noise)"
+        from lanpaint_b200 import hostnoise
+        best = float("inf")
+        for k in range(reps + 1):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            hostnoise.torch_cpu_randn(self.latent["samples"].size(), 7 + k, dev)
+            torch.cuda.synchronize(dev)
             best = min(best, time.perf_counter() - t0)
-        return 1e3 * best
+        return 1e3 * best, 1e3 * best_cpu, "device (hostnoise.torch_cpu_randn: the bits of ComfyUI's CPU draw)"
 
     def stats(self):
         eng = self.N.LAST_ENGINE["engine"]
@@ -487,19 +499,23 @@ def run_b200(args):
 
     # ---- main line: the node API at the shipped default -------------------------------------------------------
     main, wl_main = measure(spec_main, args.rng, K, W, J, tag="main")
-    noise_ms = wl_main.prepare_noise_ms()
+    noise_ms, cpu_noise_ms, noise_where = wl_main.prepare_noise_ms()
+    on_device = noise_where.startswith("device")
+    wl_main.h2d = wl_main.h2d - (wl_main.latent["samples"].numel() * 4 if on_device else 0)   # no noise image to upload
     value, ms_per_step = main["value"], main["ms_per_job_device"] * J
     e2e = {"value": main["e2e_value"], "unit": "sub-steps/s", "h2d_bytes_per_step": wl_main.h2d * J,
            "d2h_bytes_per_step": wl_main.d2h * J, "steps": K, "jobs_per_step": J,
            "ms_per_job_wall": main["ms_per_job_wall"],
-           "breakdown_ms_per_job": {"comfyui_prepare_noise_cpu_randn": noise_ms,
+           "breakdown_ms_per_job": {"noise_image": noise_ms, "noise_image_drawn_on": noise_where,
+                                    "comfyui_cpu_prepare_noise_it_replaces": cpu_noise_ms,
                                     "sampler_loop_on_device": main["ms_per_job_device"],
                                     "h2d_d2h_and_host_python": main["ms_per_job_wall"] - noise_ms - main["ms_per_job_device"]},
-           "pcie_gbs": {"note": "latent + noise + mask up, result down, pageable CPU tensors as ComfyUI hands them over",
+           "pcie_gbs": {"note": "latent + mask up (pageable CPU tensors as ComfyUI hands them over; the noise image too when "
+                                "it is drawn on the CPU), result down through pinned memory",
                         "bytes_per_job": wl_main.h2d + wl_main.d2h},
            "numa_node": numa,
-           "api": f"lanpaint_b200.comfy_nodes.LanPaint_KSampler.sample, rng={args.rng}, LATENT dict of pinned host tensors "
-                  "in, LATENT dict of host tensors out (every call: ComfyUI's CPU prepare_noise, H2D, sampler loop, D2H)"}
+           "api": f"lanpaint_b200.comfy_nodes.LanPaint_KSampler.sample, rng={args.rng}, LATENT dict of host tensors in, LATENT "
+                  "dict of host tensors out (every call: the noise image of comfy.sample.prepare_noise, H2D, sampler loop, D2H)"}
     launches = (wl_main.stats()["graph_nodes_per_job"] or 0) * K * J * world
 
     # ---- secondary records: an exception in any of them is reported in the line, never in place of it ----------

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define LP_ABI_VERSION 4
+#define LP_ABI_VERSION 5
 #define LP_TABLE_STRIDE 32 /* floats per table row (one 128-byte line), layout below */
 
 typedef void* lp_stream_t; /* a cudaStream_t / CUstream */
@@ -300,6 +300,19 @@ int lp_stop_stats_f32(const float* a, const float* b, const uint8_t* mask, const
 /* ---- device: utilities (tests, bench) ---------------------------------- */
 /* out[i] ~ N(0,1) with the given rng (PHILOX or TORCH; draw0 only). */
 int lp_fill_normal_f32(float* out, int64_t n, const lp_rng* rng, lp_stream_t stream);
+
+/* The noise image of a sample call with the bits of ComfyUI's CPU draw.  `comfy.sample.prepare_noise`, which
+ * nodes.common_ksampler calls for every LanPaint KSampler node (src/LanPaint/nodes.py:513,589), is
+ * `torch.manual_seed(seed); torch.randn(size, generator=..., device="cpu")`: at::mt19937 (one 32-bit output per
+ * float, 24 bits kept), torch's normal_fill (Box-Muller over the pairs (j, j+8) of every 16 values; a size that is
+ * not a multiple of 16 redraws its last 16) with avx_mathfun.h's cephes log / sincos as the AVX2 build executes them.
+ * Writes out[0..n) ~ N(0,1) with exactly those bits (fp32, n >= 16; `out` must have room for n + 16 floats).
+ * state_out (optional, 624 words on the device) receives the generator's state array after its last twist and
+ * *consumed_out (optional, host) the number of 32-bit outputs drawn, so that the caller can leave the host's CPU
+ * generator where ComfyUI's own call would have left it.  One CTA walks the (sequential) generator; the transform
+ * is a second, parallel launch. */
+int lp_torch_cpu_randn_f32(float* out, int64_t n, uint64_t seed, uint32_t* state_out, int64_t* consumed_out,
+                           lp_stream_t stream);
 
 /* Synthetic pointwise two-head denoiser used by bench.py:
  *   h0 = a0*x + b0*tanh(x) + c0 ;  h1 = a1*x + c1     coef = {a0,b0,c0,a1,c1} */

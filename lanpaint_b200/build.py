@@ -16,7 +16,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-SOURCES = [os.path.join(CSRC, n) for n in ("lp_substep.cu", "lp_boundary.cu", "lp_misc.cu", "lp_table.cc")]
+SOURCES = [os.path.join(CSRC, n) for n in ("lp_substep.cu", "lp_boundary.cu", "lp_misc.cu", "lp_hostnoise.cu", "lp_table.cc")]
 HEADERS = [os.path.join(ROOT, "include", "lanpaint_b200.h"), os.path.join(CSRC, "lp_common.cuh")]
 LIB_DIR = os.path.join(PKG, "_lib")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")

@@ -751,10 +751,34 @@ _override_active = False
 LAST_ENGINE = {"engine": None}  # the engine of the most recent sample call (bench/test introspection)
 
 
+def _noise_device(model, opts=None):
+    """The CUDA device a node's noise image may be drawn on instead of ComfyUI's CPU, or None: the model's load
+    device, unless `{"device_noise": False}` or this host's torch draws other bits than the kernel (hostnoise.verified)."""
+    if opts is None:
+        opts = (getattr(model, "model_options", None) or {}).get("lanpaint_b200") or {}
+    if not opts.get("device_noise", True):
+        return None
+    dev = getattr(model, "load_device", None)
+    if dev is None or torch.device(dev).type != "cuda":
+        return None
+    from . import hostnoise
+    return torch.device(dev) if hostnoise.verified(dev) else None
+
+
+def _device_randn_ok(latent_image, noise_inds=None) -> bool:
+    """What lp_torch_cpu_randn_f32 reproduces: one `torch.randn(size, fp32, strided)` of at least 16 values."""
+    return (noise_inds is None and isinstance(latent_image, torch.Tensor) and not latent_image.is_nested
+            and latent_image.dtype == torch.float32 and latent_image.layout == torch.strided and latent_image.numel() >= 16)
+
+
 @contextmanager
-def override_sample_function():
+def override_sample_function(noise_device=None):
     """Swap CFGGuider.outer_sample / .predict_noise, KSAMPLER.sample and sampler_helpers.prepare_mask for
-    the duration of one sample call; always restore; nested entry is a no-op (nodes.py:384-421)."""
+    the duration of one sample call; always restore; nested entry is a no-op (nodes.py:384-421).
+
+    With `noise_device` (a CUDA device whose stream was verified against this host's torch.randn) a fifth function
+    is swapped as well: `comfy.sample.prepare_noise`, ComfyUI's single-threaded CPU draw of the noise image, by
+    `hostnoise.torch_cpu_randn` -- the same bits, the same effect on torch's generators, drawn on the device."""
     global _override_active
     if _override_active:
         yield
@@ -762,6 +786,14 @@ def override_sample_function():
     _override_active = True
     guider_cls, ksampler_cls, helpers = comfy.samplers.CFGGuider, comfy.samplers.KSAMPLER, comfy.sampler_helpers
     saved = (guider_cls.outer_sample, guider_cls.predict_noise, ksampler_cls.sample, helpers.prepare_mask)
+    sample_mod = getattr(comfy, "sample", None) if noise_device is not None else None
+    saved_noise = getattr(sample_mod, "prepare_noise", None)
+
+    def prepare_noise_on_device(latent_image, seed, noise_inds=None):
+        if not _device_randn_ok(latent_image, noise_inds):
+            return saved_noise(latent_image, seed, noise_inds)
+        from . import hostnoise
+        return hostnoise.torch_cpu_randn(latent_image.size(), seed, noise_device)
 
     def sample_and_remember(self, *a, **k):
         out = KSAMPLER.sample(self, *a, **k)
@@ -774,9 +806,13 @@ def override_sample_function():
         ksampler_cls.sample = sample_and_remember
         helpers.prepare_mask = lambda noise_mask, shape, device: prepare_mask(
             noise_mask, shape, device, video_inpainting=(len(shape) == 5))
+        if saved_noise is not None:
+            sample_mod.prepare_noise = prepare_noise_on_device
         yield
     finally:
         guider_cls.outer_sample, guider_cls.predict_noise, ksampler_cls.sample, helpers.prepare_mask = saved
+        if saved_noise is not None:
+            sample_mod.prepare_noise = saved_noise
         _override_active = False
 
 
@@ -826,7 +862,7 @@ class LanPaint_KSampler:
         imode = _sanitize_param(Inpainting_mode, IMAGE_MODE, allowed=(IMAGE_MODE, VIDEO_MODE))
         _set_hyper(model, num_steps=n, cfg=cfg, prompt_mode=mode)
         _ensure_model_options(model, imode == VIDEO_MODE)
-        with override_sample_function():
+        with override_sample_function(_noise_device(model)):
             return comfy_nodes_module.common_ksampler(model, seed, steps, cfg, sampler_name, scheduler, positive,
                                                       negative, latent_image, denoise=denoise)
 
@@ -874,7 +910,7 @@ class LanPaint_KSamplerAdvanced:
         imode = _sanitize_param(Inpainting_mode, IMAGE_MODE, allowed=(IMAGE_MODE, VIDEO_MODE))
         _set_hyper(model, num_steps=n, cfg=cfg, prompt_mode=mode, lam=lam, step_size=step)
         _ensure_model_options(model, imode == VIDEO_MODE)
-        with override_sample_function():
+        with override_sample_function(_noise_device(model)):
             return comfy_nodes_module.common_ksampler(
                 model, noise_seed, steps, cfg, sampler_name, scheduler, positive, negative, latent_image, denoise=1.0,
                 disable_noise=(add_noise == "disable"), start_step=start_at_step, last_step=end_at_step,
@@ -887,12 +923,17 @@ class Noise_EmptyNoise:
 
 
 class Noise_RandomNoise:
-    def __init__(self, seed):
+    def __init__(self, seed, device=None):
         self.seed = seed
+        self.device = device       # a verified CUDA device (see _noise_device): same bits, drawn there
 
     def generate_noise(self, latent):
+        samples = latent["samples"]
+        if self.device is not None and _device_randn_ok(samples) and samples.device.type == "cpu":
+            from . import hostnoise
+            return hostnoise.torch_cpu_randn(samples.size(), self.seed, self.device)
         torch.manual_seed(self.seed)
-        return torch.randn_like(latent["samples"])
+        return torch.randn_like(samples)
 
 
 def _finish_custom(model_for_preview, latent, samples, x0_output):
@@ -933,10 +974,11 @@ class LanPaint_SamplerCustom:
         n = _sanitize_param(LanPaint_NumSteps, 5)
         mode = _sanitize_param(LanPaint_PromptMode, "Image First", allowed=PROMPT_MODES)
         _set_hyper(model, num_steps=n, cfg=cfg, prompt_mode=mode)
-        with override_sample_function():
+        noise_device = _noise_device(model)
+        with override_sample_function(noise_device):
             latent = latent_image.copy()
             latent["samples"] = comfy.sample.fix_empty_latent_channels(model, latent["samples"])
-            noise = (Noise_RandomNoise(noise_seed) if add_noise else Noise_EmptyNoise()).generate_noise(latent)
+            noise = (Noise_RandomNoise(noise_seed, noise_device) if add_noise else Noise_EmptyNoise()).generate_noise(latent)
             x0_output = {}
             callback = latent_preview.prepare_callback(model, sigmas.shape[-1] - 1, x0_output)
             samples = comfy.sample.sample_custom(model, noise, cfg, sampler, sigmas, positive, negative,
@@ -978,7 +1020,7 @@ class LanPaint_SamplerCustomAdvanced:
         mode = _sanitize_param(LanPaint_PromptMode, "Image First", allowed=PROMPT_MODES)
         patcher = guider.model_patcher
         _set_hyper(patcher, num_steps=n, cfg=guider.cfg, prompt_mode=mode, lam=lam, step_size=step)
-        with override_sample_function():
+        with override_sample_function(_noise_device(patcher)):      # ComfyUI's RandomNoise calls comfy.sample.prepare_noise
             latent = latent_image.copy()
             latent["samples"] = comfy.sample.fix_empty_latent_channels(patcher, latent_image["samples"])
             x0_output = {}

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_native.SYMBOLS) == declared, "binding list and header drifted apart"
-    assert lib.lp_abi_version() == _native.ABI_VERSION == 4
+    assert lib.lp_abi_version() == _native.ABI_VERSION == 5
 
 
 def test_struct_layouts_match_header():

@@ -64,7 +64,8 @@ def test_node_matches_reference_node_layer(name, cuda_device):
     patcher = build_patcher(c, device=dev, net=net)
     tape = NoiseTape([torch.from_numpy(t.astype(np.float32)) for t in g["tape"]])
     # the tape is the engine's Gaussian stream; plain launches (a tape cannot be replayed from a captured graph)
-    patcher.model_options["lanpaint_b200"] = {"rng": tape, "cuda_graph": False}
+    # (and ComfyUI's CPU noise image comes from the fixture, not from the device-side draw of this host's stream)
+    patcher.model_options["lanpaint_b200"] = {"rng": tape, "cuda_graph": False, "device_noise": False}
     latent = {"samples": torch.from_numpy(g["samples"])}
     if "noise_mask" in g:
         latent["noise_mask"] = torch.from_numpy(g["noise_mask"].astype(np.float32))
