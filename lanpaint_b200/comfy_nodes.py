@@ -788,6 +788,9 @@ def override_sample_function(noise_device=None):
     saved = (guider_cls.outer_sample, guider_cls.predict_noise, ksampler_cls.sample, helpers.prepare_mask)
     sample_mod = getattr(comfy, "sample", None) if noise_device is not None else None
     saved_noise = getattr(sample_mod, "prepare_noise", None)
+    if not (getattr(saved_noise, "__name__", "") == "prepare_noise"
+            and getattr(saved_noise, "__module__", "") in ("comfy.sample", "minicomfy")):
+        saved_noise = None      # some extension installed its own noise source: that is what the user asked for
 
     def prepare_noise_on_device(latent_image, seed, noise_inds=None):
         if not _device_randn_ok(latent_image, noise_inds):

@@ -17,35 +17,47 @@
 //     self-checks once per process and leaves ComfyUI's own function in place if the host's torch draws other bits).
 //
 // MT19937 is one sequential recurrence, x[n] = x[n-227] ^ twist(x[n-624], x[n-623]).  Column c of a "row" of 227
-// consecutive words depends on the same column of the previous row (same thread) and on two words 2.7 rows back
-// (other threads): ONE CTA walks the stream with 227 threads, the last 2048 words in a shared-memory ring, one
-// barrier per TWO rows.  The transform is a separate, fully parallel launch.
+// consecutive words depends on the same column of the previous row (same thread, a register) and on two words 2.7
+// rows back (other threads): ONE CTA walks the stream with 227 threads, the last 2048 words in a shared-memory ring,
+// one barrier per TWO rows, and stores the raw words; tempering, the conversion to a uniform and the Box-Muller
+// transform are a second, fully parallel launch.
 #include "lp_common.cuh"
 
 namespace lp {
 
 constexpr int kMtN = 624, kMtM = 397, kMtLag = kMtN - kMtM;  // 227
-constexpr int kMtRing = 2048;                                  // >= 624 + 2*227 + slack, power of two
-constexpr int kMtThreads = 256;
+constexpr int kMtRing = 2048;                                  // power of two; see the hazard argument below
+constexpr int kMtMask = kMtRing - 1;
+constexpr int kMtThreads = 256;                                // 227 of them walk the recurrence
+constexpr int kMtSpan = 2 * kMtLag;                            // words per barrier interval (two rows)
 
 __device__ __forceinline__ uint32_t mt_twist(uint32_t u, uint32_t v) {
   const uint32_t y = (u & 0x80000000u) | (v & 0x7fffffffu);
-  return (y >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+  return (y >> 1) ^ ((0u - (v & 1u)) & 0x9908b0dfu);
 }
 
+// tempering + at::uniform_real_distribution<float>: 24 bits of the output times 2^-24 (exact)
 __device__ __forceinline__ float mt_uniform(uint32_t y) {
   y ^= (y >> 11);
   y ^= (y << 7) & 0x9d2c5680u;
   y ^= (y << 15) & 0xefc60000u;
   y ^= (y >> 18);
-  return __uint2float_rn(y & 0x00ffffffu) * 5.9604644775390625e-08f;  // exact: 24 bits times 2^-24
+  return __uint2float_rn(y & 0x00ffffffu) * 5.9604644775390625e-08f;
 }
 
-// out[i] = uniform of the i-th generator output for i < n_out; words are generated up to n_words (a multiple of 624,
+// raw[i] = the i-th generator word BEFORE tempering, for i < n_out (the parallel transform kernel tempers: nothing
+// that can be done elsewhere stays on the sequential path); words are generated through n_words (a multiple of 624,
 // >= n_out) so that state_out receives the engine's complete state array after its last twist.
-__global__ void __launch_bounds__(kMtThreads, 1) mt19937_uniform_kernel(float* __restrict__ out, int64_t n_out,
-                                                                          int64_t n_words, uint32_t seed,
-                                                                          uint32_t* __restrict__ state_out) {
+//
+// With X = i + 624 the index of word i in the sequence that starts with the seeded state x[0..623], at::mt19937 is
+// x[X] = x[X-227] ^ twist(x[X-624], x[X-623]).  Thread c owns column c of every "row" of 227 words: x[X-227] is its own
+// previous result (a register), x[X-624] / x[X-623] were written two to three rows earlier by other threads.  So two rows
+// are produced between barriers.  Ring of 2048 words: within one interval the threads write x-indices
+// [624 + 454 t, 624 + 454 t + 453] and read [454 t, 454 t + 454]: no two of these are 2048 apart, and a slot is
+// overwritten 4.5 intervals after it was written.
+__global__ void __launch_bounds__(kMtThreads, 1) mt19937_raw_kernel(uint32_t* __restrict__ raw, int64_t n_out,
+                                                                      int64_t n_words, uint32_t seed,
+                                                                      uint32_t* __restrict__ state_out) {
   __shared__ uint32_t ring[kMtRing];
   pdl_prologue();
   const int c = threadIdx.x;
@@ -58,22 +70,51 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt19937_uniform_kernel(float* _
     }
   }
   __syncthreads();
-  // x[kMtN + i] is generator output i (before tempering).  Row r covers outputs [227 r, 227 r + 227).
-  const int64_t rows = (n_words + kMtLag - 1) / kMtLag;
-  for (int64_t r = 0; r < rows; r += 2) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int64_t i = (r + h) * kMtLag + c;   // output index of this thread in this row
-      if (c < kMtLag && i < n_words) {
-        const uint32_t n = (uint32_t)((i + kMtN) & (kMtRing - 1));
-        const uint32_t a = ring[(n - kMtN) & (kMtRing - 1)];
-        const uint32_t b = ring[(n - kMtN + 1) & (kMtRing - 1)];
-        const uint32_t m = ring[(n - kMtLag) & (kMtRing - 1)];
-        const uint32_t x = m ^ mt_twist(a, b);
-        ring[n] = x;
-        if (i < n_out) out[i] = mt_uniform(x);
-        if (state_out && i >= n_words - kMtN) state_out[i - (n_words - kMtN)] = x;
+  const int64_t intervals = (n_words + kMtSpan - 1) / kMtSpan;
+  const int64_t state_lo = n_words - kMtN;
+  // intervals that lie entirely inside raw[0, n_out) and before the state block: no bounds to test in the hot loop
+  int64_t fast = n_out / kMtSpan;
+  if (state_out && state_lo / kMtSpan < fast) fast = state_lo / kMtSpan;
+  const bool active = c < kMtLag;
+  uint32_t prev = active ? ring[kMtM + c] : 0u;           // x[X-227] of row 0
+  uint32_t p = (uint32_t)c;                                // ring slot of x[X-624] of this interval's first row
+  uint32_t* dst = raw + c;
+  int64_t t = 0;
+#pragma unroll 1
+  for (; t < fast; ++t) {
+    if (active) {
+      const uint32_t a0 = ring[p], b0 = ring[(p + 1) & kMtMask];
+      const uint32_t a1 = ring[(p + kMtLag) & kMtMask], b1 = ring[(p + kMtLag + 1) & kMtMask];
+      const uint32_t x0 = prev ^ mt_twist(a0, b0);
+      const uint32_t x1 = x0 ^ mt_twist(a1, b1);
+      ring[(p + kMtN) & kMtMask] = x0;
+      ring[(p + kMtN + kMtLag) & kMtMask] = x1;
+      dst[0] = x0;
+      dst[kMtLag] = x1;
+      prev = x1;
+      p = (p + kMtSpan) & kMtMask;
+      dst += kMtSpan;
+    }
+    __syncthreads();
+  }
+#pragma unroll 1
+  for (; t < intervals; ++t) {   // the last few intervals: the end of raw[], the engine's final state block
+    if (active) {
+      const uint32_t a0 = ring[p], b0 = ring[(p + 1) & kMtMask];
+      const uint32_t a1 = ring[(p + kMtLag) & kMtMask], b1 = ring[(p + kMtLag + 1) & kMtMask];
+      const uint32_t x0 = prev ^ mt_twist(a0, b0);
+      const uint32_t x1 = x0 ^ mt_twist(a1, b1);
+      ring[(p + kMtN) & kMtMask] = x0;
+      ring[(p + kMtN + kMtLag) & kMtMask] = x1;
+      const int64_t i0 = t * kMtSpan + c, i1 = i0 + kMtLag;
+      if (i0 < n_out) raw[i0] = x0;
+      if (i1 < n_out) raw[i1] = x1;
+      if (state_out) {
+        if (i0 >= state_lo && i0 < n_words) state_out[i0 - state_lo] = x0;
+        if (i1 >= state_lo && i1 < n_words) state_out[i1 - state_lo] = x1;
       }
+      prev = x1;
+      p = (p + kMtSpan) & kMtMask;
     }
     __syncthreads();
   }
@@ -136,15 +177,16 @@ __device__ __forceinline__ void cephes_sincosf_avx(float x, float& s, float& c) 
   c = __uint_as_float(__float_as_uint(poly ? yc : ys) ^ sign_cos);
 }
 
-// One thread per Box-Muller pair (j, j+8) of a 16-group.  `src` holds the uniforms of the groups, `dst` receives the
-// normals (src == dst for the body of the tensor; the redrawn tail reads the 16 extra uniforms and writes the last 16).
-__global__ void __launch_bounds__(kBlock) normal_fill16_kernel(const float* src, float* dst, int64_t n_pairs) {
+// One thread per Box-Muller pair (j, j+8) of a 16-group.  `src` holds the raw generator words of the group, `dst`
+// receives the normals (src == dst for the body of the tensor; the redrawn tail reads the 16 extra words and writes the
+// last 16 values).
+__global__ void __launch_bounds__(kBlock) normal_fill16_kernel(const uint32_t* src, float* dst, int64_t n_pairs) {
   pdl_prologue();
   const int64_t p = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   if (p >= n_pairs) return;
   const int64_t i = (p >> 3) * 16 + (p & 7);
-  const float u1 = __fsub_rn(1.0f, src[i]);   // [0,1) -> (0,1]
-  const float u2 = src[i + 8];
+  const float u1 = __fsub_rn(1.0f, mt_uniform(src[i]));   // [0,1) -> (0,1]
+  const float u2 = mt_uniform(src[i + 8]);
   const float radius = __fsqrt_rn(__fmul_rn(-2.0f, cephes_logf_avx(u1)));
   const float theta = __fmul_rn(6.2831854820251465f, u2);   // float(2 * pi<double>)
   float s, c;
@@ -166,14 +208,15 @@ extern "C" int lp_torch_cpu_randn_f32(float* out, int64_t n, uint64_t seed, uint
   const int64_t consumed = n + tail;
   const int64_t n_words = ((consumed + kMtN - 1) / kMtN) * kMtN;   // through the end of the engine's current block
   if (consumed_out) *consumed_out = consumed;
-  launch_kernel_ex(mt19937_uniform_kernel, dim3(1), dim3(kMtThreads), 0, s, out, consumed, n_words,
+  launch_kernel_ex(mt19937_raw_kernel, dim3(1), dim3(kMtThreads), 0, s, reinterpret_cast<uint32_t*>(out), consumed, n_words,
                    (uint32_t)(seed & 0xffffffffull), state_out);
   if (int rc = check_launch()) return rc;
   const int64_t pairs = (n / 16) * 8;
-  launch_kernel(normal_fill16_kernel, dim3((unsigned)((pairs + kBlock - 1) / kBlock)), s, (const float*)out, out, pairs);
+  launch_kernel(normal_fill16_kernel, dim3((unsigned)((pairs + kBlock - 1) / kBlock)), s,
+                reinterpret_cast<const uint32_t*>(out), out, pairs);
   if (int rc = check_launch()) return rc;
   if (tail) {
-    launch_kernel(normal_fill16_kernel, dim3(1), s, (const float*)(out + n), out + n - 16, (int64_t)8);
+    launch_kernel(normal_fill16_kernel, dim3(1), s, reinterpret_cast<const uint32_t*>(out + n), out + n - 16, (int64_t)8);
     if (int rc = check_launch()) return rc;
   }
   return LP_OK;

@@ -4,6 +4,7 @@
 oracle here is torch itself on this host -- for whole 16-groups, redrawn tails, seeds above 2^32, and sizes that
 span many twists of the generator; the wrapper must leave torch's CPU and CUDA generators where ComfyUI's call leaves
 them; and a node call that draws its noise on the device must return the latent of one that lets ComfyUI draw it."""
+import functools
 import sys
 import time
 
@@ -87,6 +88,7 @@ def test_node_call_is_unchanged_by_where_the_noise_is_drawn(node, cuda_device):
     for device_noise in (True, False):
         n_cpu = {"n": 0}
 
+        @functools.wraps(real)       # still ComfyUI's stock function as far as the patch layer can tell
         def counting(latent_image, seed, noise_inds=None):
             n_cpu["n"] += 1
             return real(latent_image, seed, noise_inds)
@@ -117,7 +119,8 @@ def test_what_the_kernel_does_not_cover_goes_to_comfyui(cuda_device):
     from lanpaint_b200 import comfy_nodes as N
     seen = []
     real = sys.modules["comfy.sample"].prepare_noise
-    sys.modules["comfy.sample"].prepare_noise = lambda *a, **k: (seen.append(a[0].shape), real(*a, **k))[1]
+    spy = functools.wraps(real)(lambda *a, **k: (seen.append(a[0].shape), real(*a, **k))[1])
+    sys.modules["comfy.sample"].prepare_noise = spy
     try:
         with N.override_sample_function(cuda_device):
             fn = sys.modules["comfy.sample"].prepare_noise
@@ -127,5 +130,22 @@ def test_what_the_kernel_does_not_cover_goes_to_comfyui(cuda_device):
             d = fn(torch.zeros(1, 4, 8, 8), 5)
         assert len(seen) == 3 and a.device.type == b.device.type == c.device.type == "cpu" and d.is_cuda
         assert torch.equal(d.cpu(), real(torch.zeros(1, 4, 8, 8), 5))
+    finally:
+        sys.modules["comfy.sample"].prepare_noise = real
+
+
+def test_a_foreign_noise_source_is_left_alone(cuda_device):
+    """An extension that replaced comfy.sample.prepare_noise (GPU noise, other RNGs ...) keeps working inside a
+    LanPaint node: only ComfyUI's stock function is swapped for the device draw."""
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    real = sys.modules["comfy.sample"].prepare_noise
+
+    def their_noise(latent_image, seed, noise_inds=None):
+        return torch.full_like(latent_image, 0.25)
+    sys.modules["comfy.sample"].prepare_noise = their_noise
+    try:
+        with N.override_sample_function(cuda_device):
+            assert sys.modules["comfy.sample"].prepare_noise is their_noise
     finally:
         sys.modules["comfy.sample"].prepare_noise = real
