@@ -75,28 +75,39 @@ __global__ void __launch_bounds__(kMtThreads, 1) mt19937_raw_kernel(uint32_t* __
   // intervals that lie entirely inside raw[0, n_out) and before the state block: no bounds to test in the hot loop
   int64_t fast = n_out / kMtSpan;
   if (state_out && state_lo / kMtSpan < fast) fast = state_lo / kMtSpan;
-  const bool active = c < kMtLag;
-  uint32_t prev = active ? ring[kMtM + c] : 0u;           // x[X-227] of row 0
-  uint32_t p = (uint32_t)c;                                // ring slot of x[X-624] of this interval's first row
-  uint32_t* dst = raw + c;
+  // threads 227..255 shadow column 226 (same loads, same values, no stores): the hot loop has no divergent branch
+  const int col = c < kMtLag ? c : kMtLag - 1;
+  const bool owner = c < kMtLag;
+  uint32_t prev = ring[kMtM + col];                        // x[X-227] of row 0
+  uint32_t p = (uint32_t)col;                              // ring slot of x[X-624] of this interval's first row
+  const uint32_t base = smem_u32(ring);                    // shared-window address, computed once
+  uint32_t* dst = raw + col;
   int64_t t = 0;
+  for (int64_t left = fast; left > 0; left -= (left > 0x40000000 ? 0x40000000 : left)) {
+    const int chunk = (int)(left > 0x40000000 ? 0x40000000 : left);   // 32-bit trip count for the hot loop
 #pragma unroll 1
-  for (; t < fast; ++t) {
-    if (active) {
-      const uint32_t a0 = ring[p], b0 = ring[(p + 1) & kMtMask];
-      const uint32_t a1 = ring[(p + kMtLag) & kMtMask], b1 = ring[(p + kMtLag + 1) & kMtMask];
+    for (int k = 0; k < chunk; ++k) {
+      uint32_t a0, b0, a1, b1;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a0) : "r"(base + 4u * p));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b0) : "r"(base + 4u * ((p + 1) & kMtMask)));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a1) : "r"(base + 4u * ((p + kMtLag) & kMtMask)));
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(b1) : "r"(base + 4u * ((p + kMtLag + 1) & kMtMask)));
       const uint32_t x0 = prev ^ mt_twist(a0, b0);
       const uint32_t x1 = x0 ^ mt_twist(a1, b1);
-      ring[(p + kMtN) & kMtMask] = x0;
-      ring[(p + kMtN + kMtLag) & kMtMask] = x1;
-      dst[0] = x0;
-      dst[kMtLag] = x1;
+      if (owner) {   // predicated stores, no divergence: the shadow lanes only keep the warp converged
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 4u * ((p + kMtN) & kMtMask)), "r"(x0) : "memory");
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + 4u * ((p + kMtN + kMtLag) & kMtMask)), "r"(x1) : "memory");
+        dst[0] = x0;
+        dst[kMtLag] = x1;
+      }
       prev = x1;
       p = (p + kMtSpan) & kMtMask;
       dst += kMtSpan;
+      __syncthreads();
     }
-    __syncthreads();
+    t += chunk;
   }
+  const bool active = owner;
 #pragma unroll 1
   for (; t < intervals; ++t) {   // the last few intervals: the end of raw[], the engine's final state block
     if (active) {
