@@ -89,7 +89,8 @@ def torch_cpu_randn(shape: Sequence[int], seed: int, device, advance_cpu_generat
 
 def verified(device) -> bool:
     """True when the device stream equals THIS host's `torch.randn` (a body of whole 16-groups and a redrawn
-    tail, two seeds, one of them above 2^32).  Checked once per process and device; never raises."""
+    tail, two seeds, one of them above 2^32) and the generator bookkeeping reproduces the state torch's own draw
+    leaves behind.  Checked once per process and device; never raises."""
     device = torch.device(device)
     key = device.index if device.index is not None else (torch.cuda.current_device() if device.type == "cuda" else -1)
     hit = _verified.get(key)
@@ -100,9 +101,14 @@ def verified(device) -> bool:
         if device.type == "cuda":
             ok = True
             for seed, n in ((0x5EED, 8192), (0x9E3779B97F4A7C15, 4096 + 8)):
-                want = torch.randn(n, generator=torch.Generator().manual_seed(seed), dtype=torch.float32, device="cpu")
-                got, _, consumed = _draw(n, seed, device)
+                ref = torch.Generator().manual_seed(seed)
+                want = torch.randn(n, generator=ref, dtype=torch.float32, device="cpu")
+                got, state, consumed = _draw(n, seed, device)
                 ok = ok and consumed == n + (16 if n % 16 else 0) and torch.equal(got[:n].cpu(), want)
+                # ... and this torch's CPU generator state has the layout _advance_cpu_generator writes
+                mine = torch.Generator().manual_seed(seed)
+                _advance_cpu_generator(mine, state, consumed)
+                ok = ok and torch.equal(mine.get_state(), ref.get_state())
     except Exception:
         ok = False
     _verified[key] = ok

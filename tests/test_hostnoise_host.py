@@ -41,3 +41,24 @@ def test_there_is_no_cpu_path():
     with pytest.raises(RuntimeError):
         H.torch_cpu_randn((4, 4), 1, "cpu")
     assert H.verified("cpu") is False
+
+
+def test_what_the_node_layer_hands_to_the_kernel():
+    """one fp32, strided draw of at least 16 values without batch_index noise; and never without a CUDA device"""
+    import minicomfy
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    ok = torch.zeros(1, 4, 8, 8)
+    assert N._device_randn_ok(ok) and not N._device_randn_ok(ok, [0, 1])
+    assert not N._device_randn_ok(ok.double()) and not N._device_randn_ok(torch.zeros(1, 1, 3, 3))
+    assert not N._device_randn_ok(None)
+    patcher = minicomfy.ModelPatcher(minicomfy.BaseModel(lambda x, s, c: x), "cpu")
+    assert N._noise_device(patcher) is None                    # the model does not live on a GPU
+    patcher.load_device = torch.device("cuda", 0)
+    patcher.model_options["lanpaint_b200"] = {"device_noise": False}
+    assert N._noise_device(patcher) is None                    # switched off: ComfyUI's own prepare_noise
+    # with no verified device nothing is swapped beyond the reference's four functions
+    import sys
+    stock = sys.modules["comfy.sample"].prepare_noise
+    with N.override_sample_function(None):
+        assert sys.modules["comfy.sample"].prepare_noise is stock
