@@ -800,6 +800,8 @@ def run_b200(args):
                                 else "oracle port")}
 
     except Exception as e:
+        if world > 1:      # the other ranks are inside collectives of the same section: fail fast instead of hanging them
+            raise
         import traceback
         secondary_error = f"{type(e).__name__}: {e} @ " + traceback.format_exc().strip().splitlines()[-3].strip()
 
