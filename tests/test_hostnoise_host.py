@@ -62,3 +62,30 @@ def test_what_the_node_layer_hands_to_the_kernel():
     stock = sys.modules["comfy.sample"].prepare_noise
     with N.override_sample_function(None):
         assert sys.modules["comfy.sample"].prepare_noise is stock
+
+
+def test_fifth_swap_is_scoped_like_the_other_four():
+    """With a noise device the stock prepare_noise is swapped for the duration of the call only -- restored on normal
+    exit, on an exception, and never captured as an "original" by a nested entry (nodes.py:384-421 semantics)."""
+    import sys
+
+    import minicomfy
+    minicomfy.install()
+    from lanpaint_b200 import comfy_nodes as N
+    mod = sys.modules["comfy.sample"]
+    stock = mod.prepare_noise
+    dev = torch.device("cuda", 0)                 # only installed here, never called: no GPU needed
+    with N.override_sample_function(dev):
+        swapped = mod.prepare_noise
+        assert swapped is not stock
+        with N.override_sample_function(dev):     # nested entry: a no-op
+            assert mod.prepare_noise is swapped
+        assert mod.prepare_noise is swapped
+        # what the kernel does not cover is handed to ComfyUI's own function even while swapped
+        out = swapped(torch.zeros(1, 4, 4, 4), 3, [0])
+        assert out.device.type == "cpu" and torch.equal(out, stock(torch.zeros(1, 4, 4, 4), 3, [0]))
+    assert mod.prepare_noise is stock
+    with pytest.raises(KeyError):
+        with N.override_sample_function(dev):
+            raise KeyError("boom")
+    assert mod.prepare_noise is stock
