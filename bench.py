@@ -516,7 +516,8 @@ def run_b200(args):
            "numa_node": numa,
            "api": f"lanpaint_b200.comfy_nodes.LanPaint_KSampler.sample, rng={args.rng}, LATENT dict of host tensors in, LATENT "
                   "dict of host tensors out (every call: the noise image of comfy.sample.prepare_noise, H2D, sampler loop, D2H)"}
-    launches = (wl_main.stats()["graph_nodes_per_job"] or 0) * K * J * world
+    # kernels of this repository launched inside the timed region: the job's graph nodes + the two noise-image kernels
+    launches = ((wl_main.stats()["graph_nodes_per_job"] or 0) + (2 if on_device else 0)) * K * J * world
 
     # ---- secondary records: an exception in any of them is reported in the line, never in place of it ----------
     variants, serving, roofs, configs, other_sampler, real_network, frame_shard, cpu = {}, None, {}, None, None, None, None, None
