@@ -13,7 +13,10 @@ import torch
 
 import minicomfy
 
-pytestmark = pytest.mark.gpu
+# torch's CPU randn draws the avx_mathfun bits on every x86 host with AVX2 (the AVX512 dispatch falls back to that
+# kernel); on anything else the device draw is never enabled (hostnoise.verified) and there is nothing to compare
+_AVX2_HOST = torch.backends.cpu.get_cpu_capability() in ("AVX2", "AVX512")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not _AVX2_HOST, reason="this host's torch.randn is not the AVX2 stream")]
 
 
 def _cpu(shape, seed):
