@@ -10,6 +10,9 @@ recorded noise tape, so every fixture carries: the inputs, the tape, the
 returned `out`, and the in-place-rewritten `x`.  `/root/reference` does not
 exist on the GPU box, so nothing but this script reads it.
 
+Node-level fixtures (the reference's own nodes.py driven over minicomfy: node_*.npz) come from the sibling script
+tests/golden/make_node_golden.py.
+
 Fixture format (npz): x, y, noise, sigma, mask, ve, abt, flow_t, tape[k,...],
 out, x_new, meta (json string: hyper-parameters, model kind, n_steps, flags).
 """
