@@ -13,8 +13,13 @@ patched for the duration of one sample call and their restore-on-exception
 What is different: the per-sigma wrapper computes the schedule on the host
 from ONE read-back of sigma (the reference syncs twice per outer step plus
 once per sub-step), caches the packed mask across outer steps, and calls the
-fused engine (`lanpaint_b200.engine.LanPaint`).  Only the four sampler nodes
-exist here: mask/video/audio tooling is outside the hot path.
+fused engine (`lanpaint_b200.engine.LanPaint`).  Around the sampler loop, two
+costs that dwarf it at large batches are taken over as well: the result goes
+back to the host through pinned memory (`_host_result`), and -- when this
+host's torch.randn was verified to draw the same bits -- ComfyUI's CPU noise
+image (`comfy.sample.prepare_noise`) is drawn on the device (`hostnoise.py`; a
+fifth, optional swap in `override_sample_function`).  Only the four sampler
+nodes exist here: mask/video/audio tooling is outside the hot path.
 """
 from __future__ import annotations
 
